@@ -1,0 +1,86 @@
+// Context, error reporting and TMA descriptor encoding for libnbest_sm100.so.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "common.h"
+
+void nbest_set_error(nbest_ctx* ctx, const char* fmt, ...) {
+  if (!ctx) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int nbest_abi_version(void) { return NBEST_ABI_VERSION; }
+
+static __thread char g_create_err[256];
+
+extern "C" int nbest_ctx_create(nbest_ctx** out, int device) {
+  if (!out) return NBEST_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    snprintf(g_create_err, sizeof(g_create_err), "no CUDA device: %s", cudaGetErrorString(e));
+    return NBEST_ECUDA;  // no CPU fallback: the hot path exists only on the GPU
+  }
+  if (device < 0 || device >= ndev) return NBEST_EINVAL;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NBEST_ECUDA;
+  if (prop.major != 10) {
+    snprintf(g_create_err, sizeof(g_create_err), "device %d is sm_%d%d, this library is sm_100a only", device, prop.major,
+             prop.minor);
+    return NBEST_EUNSUPPORTED;
+  }
+  nbest_ctx* ctx = (nbest_ctx*)calloc(1, sizeof(nbest_ctx));
+  if (!ctx) return NBEST_EINVAL;
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    free(ctx);
+    return NBEST_ECUDA;
+  }
+  cudaFree(0);  // make sure the primary context exists before asking for driver entry points
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    snprintf(g_create_err, sizeof(g_create_err), "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+    free(ctx);
+    return NBEST_ECUDA;
+  }
+  ctx->encode_tiled = (nbest_encode_tiled_fn)fn;
+  ctx->err[0] = 0;
+  *out = ctx;
+  return NBEST_OK;
+}
+
+extern "C" void nbest_ctx_destroy(nbest_ctx* ctx) { free(ctx); }
+
+extern "C" const char* nbest_last_error(nbest_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+extern "C" uint64_t nbest_launch_count(nbest_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int nbest_make_tmap_bf16(nbest_ctx* ctx, CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                         uint32_t box_rows) {
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};  // bytes, dimension 1
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (gstride[0] & 15) != 0) {
+    nbest_set_error(ctx, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+    return NBEST_EINVAL;
+  }
+  CUresult r = ctx->encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    nbest_set_error(ctx, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box_rows=%u)", (int)r,
+                    (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+    return NBEST_ECUDA;
+  }
+  return NBEST_OK;
+}

@@ -1,0 +1,442 @@
+// tcgen05 / TMEM bf16 GEMM for sm_100a, fed by TMA, persistent and warp-specialised.
+//
+// Replaces the nn.Linear calls inside the HF encoder that models/model.py:43-58 (reference) drives:
+// BertSelfAttention q/k/v (transformers modeling_bert.py:179-181), BertSelfOutput.dense (:294-298),
+// BertIntermediate.dense + GELU (:339-342), BertOutput.dense (:352-356), and their autograd products
+// (dgrad / wgrad of n_best_asr_bert.py:264 `total_loss.backward()`).
+//
+// One CTA per SM (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
+// warps 2..5 = epilogue (one TMEM lane quarter each). Tiles are 128 x BN (BN = 256 or 128) x 64, the smem ring has
+// 4 (BN=256) or 6 (BN=128) stages of 128-byte-swizzled operand tiles, and the fp32 accumulator is double buffered
+// in TMEM (2*BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Operand majorness is a template flag: K-major operands are read as {64 x rows} TMA boxes (one per stage), MN-major
+// operands (dgrad weights, both wgrad operands) as 64-column x 64-k-row boxes laid out as the canonical MN-major
+// SWIZZLE_128B UMMA layout (LBO = 8 KiB between 64-element chunks, SBO = 1 KiB between 8-row groups).
+#include "common.h"
+#include "ptx.cuh"
+
+using namespace nbest;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 2;
+constexpr uint32_t kChunkBytes = 64 * BK * 2;  // one 64-row (or 64-col) x 64 bf16 box = 8 KiB
+
+struct GemmArgs {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, num_splits, kb_per_split, num_kb;
+  void* C;
+  int64_t ldc;
+  const float* bias;
+  const __nv_bfloat16* aux;
+  int64_t ldaux;
+  __nv_bfloat16* out2;
+  uint32_t drop_thresh;
+  float drop_scale;
+  uint32_t seed;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t kABytes = BM * BK * 2;
+  static constexpr uint32_t kBBytes = BN * BK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kStagingBytes = 4 * 2048;  // 4 epilogue warps x (32 rows x 64 B)
+  static constexpr uint32_t kBarOffset = kStages * kStageBytes + kStagingBytes;
+  static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+  static constexpr uint32_t kTmemCols = 2 * BN;
+};
+
+__device__ __forceinline__ uint32_t stage_off(int row, int seg) { return row * 64 + ((seg ^ ((row >> 1) & 3)) << 4); }
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  using C_ = Cfg<BN>;
+  constexpr int kStages = C_::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + kStages * C_::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C_::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_work = g.num_m_tiles * g.num_n_tiles * g.num_splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C_::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    uint32_t stage = 0, phase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int split = w % g.num_splits;
+      const int tile = w / g.num_splits;
+      const int m0 = (tile / g.num_n_tiles) * BM;
+      const int n0 = (tile % g.num_n_tiles) * BN;
+      const int kb0 = split * g.kb_per_split;
+      const int kb1 = min(kb0 + g.kb_per_split, g.num_kb);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          uint8_t* sa = smem + stage * C_::kStageBytes;
+          uint8_t* sb = sa + C_::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], C_::kStageBytes);
+          if constexpr (!A_MN) {
+            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(&tmA, &full_bar[stage], sa + c * kChunkBytes, m0 + c * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(&tmB, &full_bar[stage], sb + c * kChunkBytes, n0 + c * 64, kb * BK);
+          }
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t a_lbo = A_MN ? kChunkBytes : 16, b_lbo = B_MN ? kChunkBytes : 16;
+    constexpr uint32_t a_kstep = A_MN ? 2048 : 32, b_kstep = B_MN ? 2048 : 32;  // bytes per UMMA_K = 16
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      const int split = w % g.num_splits;
+      const int kb0 = split * g.kb_per_split;
+      const int kb1 = min(kb0 + g.kb_per_split, g.num_kb);
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * C_::kStageBytes);
+          const uint32_t sb = sa + C_::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = umma_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = umma_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                 // frees the smem slot once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps, one TMEM lane quarter each)
+    const int q = warp & 3;  // tcgen05.ld: warp w may only touch lanes [32*(w%4), 32*(w%4)+32)
+    uint8_t* st = staging + (warp - kEpiWarp0) * 2048;
+    const uint32_t st_u32 = smem_u32(st);
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      const int tile = w / g.num_splits;
+      const int m0 = (tile / g.num_n_tiles) * BM;
+      const int n0 = (tile % g.num_n_tiles) * BN;
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const int row = m0 + q * 32 + lane;  // the accumulator row this thread owns
+      constexpr bool kHasAux = (EPI == NBEST_EPI_BIAS_DROP_RES || EPI == NBEST_EPI_DGELU || EPI == NBEST_EPI_ADD);
+      // coalesced access pattern for aux loads / C stores: 8 rows x 64 B per warp instruction
+      const int crow = lane >> 2, cseg = lane & 3;
+      uint4 aux_next[4];
+      if constexpr (kHasAux) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int gr = m0 + q * 32 + i * 8 + crow;
+          aux_next[i] = make_uint4(0, 0, 0, 0);
+          if (gr < g.M) aux_next[i] = __ldg(reinterpret_cast<const uint4*>(g.aux + (int64_t)gr * g.ldaux + n0 + cseg * 8));
+        }
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int nc = n0 + c * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + c * 32, r);
+        uint32_t auxrow[16];
+        if constexpr (kHasAux) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(st + stage_off(i * 8 + crow, cseg)) = aux_next[i];
+          if (c + 1 < BN / 32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int gr = m0 + q * 32 + i * 8 + crow;
+              aux_next[i] = make_uint4(0, 0, 0, 0);
+              if (gr < g.M)
+                aux_next[i] = __ldg(reinterpret_cast<const uint4*>(g.aux + (int64_t)gr * g.ldaux + nc + 32 + cseg * 8));
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const uint4 v = *reinterpret_cast<const uint4*>(st + stage_off(lane, s));
+            auxrow[s * 4 + 0] = v.x;
+            auxrow[s * 4 + 1] = v.y;
+            auxrow[s * 4 + 2] = v.z;
+            auxrow[s * 4 + 3] = v.w;
+          }
+          __syncwarp();
+        }
+        tmem_ld_wait();
+
+        if constexpr (EPI == NBEST_EPI_ACCUM_F32) {
+          float* crow_ptr = reinterpret_cast<float*>(g.C) + (int64_t)row * g.ldc + nc;
+          if (row < g.M) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4(crow_ptr + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                         __uint_as_float(r[j + 3]));
+          }
+        } else {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if constexpr (EPI == NBEST_EPI_BIAS || EPI == NBEST_EPI_BIAS_GELU || EPI == NBEST_EPI_BIAS_DROP_RES) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + nc + j));
+              v[j] += b.x;
+              v[j + 1] += b.y;
+              v[j + 2] += b.z;
+              v[j + 3] += b.w;
+            }
+          }
+          uint32_t packed[16];
+          if constexpr (EPI == NBEST_EPI_BIAS_GELU) {
+            if (g.out2 != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+              for (int s = 0; s < 4; ++s)
+                *reinterpret_cast<uint4*>(st + stage_off(lane, s)) =
+                    make_uint4(packed[s * 4], packed[s * 4 + 1], packed[s * 4 + 2], packed[s * 4 + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int gr = m0 + q * 32 + i * 8 + crow;
+                const uint4 o = *reinterpret_cast<const uint4*>(st + stage_off(i * 8 + crow, cseg));
+                if (gr < g.M) *reinterpret_cast<uint4*>(g.out2 + (int64_t)gr * g.ldc + nc + cseg * 8) = o;
+              }
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_fwd(v[j]);
+          } else if constexpr (EPI == NBEST_EPI_BIAS_DROP_RES) {
+            if (g.drop_thresh != 0) {
+              const uint32_t base = (uint32_t)row * (uint32_t)g.N + (uint32_t)nc;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = dropout_keep(g.seed, base + j, g.drop_thresh) ? v[j] * g.drop_scale : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[2 * j] += bf16lo(auxrow[j]);
+              v[2 * j + 1] += bf16hi(auxrow[j]);
+            }
+          } else if constexpr (EPI == NBEST_EPI_DGELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[2 * j] *= gelu_grad(bf16lo(auxrow[j]));
+              v[2 * j + 1] *= gelu_grad(bf16hi(auxrow[j]));
+            }
+          } else if constexpr (EPI == NBEST_EPI_ADD) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[2 * j] += bf16lo(auxrow[j]);
+              v[2 * j + 1] += bf16hi(auxrow[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+          for (int s = 0; s < 4; ++s)
+            *reinterpret_cast<uint4*>(st + stage_off(lane, s)) =
+                make_uint4(packed[s * 4], packed[s * 4 + 1], packed[s * 4 + 2], packed[s * 4 + 3]);
+          __syncwarp();
+          __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(g.C);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int gr = m0 + q * 32 + i * 8 + crow;
+            const uint4 o = *reinterpret_cast<const uint4*>(st + stage_off(i * 8 + crow, cseg));
+            if (gr < g.M) *reinterpret_cast<uint4*>(Cb + (int64_t)gr * g.ldc + nc + cseg * 8) = o;
+          }
+          __syncwarp();
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C_::kTmemCols);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+int launch(nbest_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
+  auto kfn = gemm_kernel<BN, A_MN, B_MN, EPI>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    NBEST_CHECK_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
+    attr_done = true;
+  }
+  const int num_work = g.num_m_tiles * g.num_n_tiles * g.num_splits;
+  const int grid = num_work < ctx->num_sms ? num_work : ctx->num_sms;
+  kfn<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(tmA, tmB, g);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
+template <int BN>
+int dispatch(nbest_ctx* ctx, int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g,
+             cudaStream_t s) {
+  if (!a_mn && !b_mn) {
+    switch (epi) {
+      case NBEST_EPI_NONE: return launch<BN, false, false, NBEST_EPI_NONE>(ctx, tmA, tmB, g, s);
+      case NBEST_EPI_BIAS: return launch<BN, false, false, NBEST_EPI_BIAS>(ctx, tmA, tmB, g, s);
+      case NBEST_EPI_BIAS_GELU: return launch<BN, false, false, NBEST_EPI_BIAS_GELU>(ctx, tmA, tmB, g, s);
+      case NBEST_EPI_BIAS_DROP_RES: return launch<BN, false, false, NBEST_EPI_BIAS_DROP_RES>(ctx, tmA, tmB, g, s);
+      default: break;
+    }
+  } else if (!a_mn && b_mn) {
+    switch (epi) {
+      case NBEST_EPI_NONE: return launch<BN, false, true, NBEST_EPI_NONE>(ctx, tmA, tmB, g, s);
+      case NBEST_EPI_DGELU: return launch<BN, false, true, NBEST_EPI_DGELU>(ctx, tmA, tmB, g, s);
+      case NBEST_EPI_ADD: return launch<BN, false, true, NBEST_EPI_ADD>(ctx, tmA, tmB, g, s);
+      default: break;
+    }
+  } else if (a_mn && b_mn) {
+    if (epi == NBEST_EPI_ACCUM_F32) return launch<BN, true, true, NBEST_EPI_ACCUM_F32>(ctx, tmA, tmB, g, s);
+  }
+  nbest_set_error(ctx, "nbest_gemm_bf16: unsupported (a_mn_major=%d, b_mn_major=%d, epilogue=%d) combination", a_mn, b_mn,
+                  epi);
+  return NBEST_EINVAL;
+}
+
+}  // namespace
+
+extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
+                               int b_mn_major, void* C, int64_t ldc, int M, int N, int K, int epilogue, const float* bias,
+                               const void* aux_bf16, int64_t ldaux, void* out2_bf16, float p_drop, uint32_t seed,
+                               void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, A && B && C, "null operand");
+  NBEST_CHECK_ARG(ctx, M > 0 && N > 0 && K > 0, "empty problem");
+  NBEST_CHECK_ARG(ctx, N % 128 == 0, "N must be a multiple of 128");
+  NBEST_CHECK_ARG(ctx, (a_mn_major && b_mn_major) || K % 64 == 0, "K must be a multiple of 64 for K-major operands");
+  NBEST_CHECK_ARG(ctx, !a_mn_major || M % 128 == 0, "M must be a multiple of 128 when A is MN-major");
+  NBEST_CHECK_ARG(ctx, ldc % 8 == 0, "ldc must be a multiple of 8");
+  const bool needs_bias =
+      epilogue == NBEST_EPI_BIAS || epilogue == NBEST_EPI_BIAS_GELU || epilogue == NBEST_EPI_BIAS_DROP_RES;
+  const bool needs_aux = epilogue == NBEST_EPI_BIAS_DROP_RES || epilogue == NBEST_EPI_DGELU || epilogue == NBEST_EPI_ADD;
+  NBEST_CHECK_ARG(ctx, !needs_bias || bias, "epilogue needs bias");
+  NBEST_CHECK_ARG(ctx, !needs_aux || (aux_bf16 && ldaux % 8 == 0), "epilogue needs aux with ldaux % 8 == 0");
+  NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
+
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  GemmArgs g;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.num_m_tiles = (M + BM - 1) / BM;
+  g.num_n_tiles = N / BN;
+  g.num_kb = (K + BK - 1) / BK;
+  g.num_splits = 1;
+  if (epilogue == NBEST_EPI_ACCUM_F32) {
+    // split the contraction so that (tiles x splits) covers about two waves of SMs, with >= 8 k-blocks per split
+    const int tiles = g.num_m_tiles * g.num_n_tiles;
+    int want = (2 * ctx->num_sms + tiles - 1) / tiles;
+    int max_by_k = g.num_kb / 8 > 0 ? g.num_kb / 8 : 1;
+    if (want > max_by_k) want = max_by_k;
+    if (want < 1) want = 1;
+    g.num_splits = want;
+  }
+  g.kb_per_split = (g.num_kb + g.num_splits - 1) / g.num_splits;
+  g.num_splits = (g.num_kb + g.kb_per_split - 1) / g.kb_per_split;  // no empty split
+  g.C = C;
+  g.ldc = ldc;
+  g.bias = bias;
+  g.aux = reinterpret_cast<const __nv_bfloat16*>(aux_bf16);
+  g.ldaux = ldaux;
+  g.out2 = reinterpret_cast<__nv_bfloat16*>(out2_bf16);
+  g.seed = seed;
+  if (p_drop > 0.f) {
+    double t = (double)p_drop * 4294967296.0;
+    g.drop_thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    g.drop_scale = 1.0f / (1.0f - p_drop);
+  } else {
+    g.drop_thresh = 0;
+    g.drop_scale = 1.0f;
+  }
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn_major)
+    rc = nbest_make_tmap_bf16(ctx, &tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM);
+  else
+    rc = nbest_make_tmap_bf16(ctx, &tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64);
+  if (rc != NBEST_OK) return rc;
+  if (!b_mn_major)
+    rc = nbest_make_tmap_bf16(ctx, &tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)BN);
+  else
+    rc = nbest_make_tmap_bf16(ctx, &tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64);
+  if (rc != NBEST_OK) return rc;
+
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (BN == 256) return dispatch<256>(ctx, a_mn_major, b_mn_major, epilogue, tmA, tmB, g, s);
+  return dispatch<128>(ctx, a_mn_major, b_mn_major, epilogue, tmA, tmB, g, s);
+}
