@@ -1,0 +1,446 @@
+// Fused masked self-attention over packed variable-length sequences (flash style), forward and backward.
+//
+// Replaces BertSelfAttention's scores / softmax / dropout / context (transformers modeling_bert.py:115-140,192-205)
+// under the key mask `attention_mask = input_ids > 0` of models/model.py:43,45. Sequences are addressed through
+// cu_seqlens, so padding does no work; the mask is "key inside the sequence AND key_valid[t]" (key_valid carries the
+// reference's XLM-R quirk that <s>=0 is masked as a key).
+//
+// DSTC2 n-best sequences are short (mean 46 tokens, <= 128 for training, <= 512 for 10-best inference), so one CTA
+// (4 warps) owns a 64-row block of one (sequence, head) and walks 64-key blocks with warp-level m16n8k16 bf16 MMAs,
+// fp32 online softmax and swizzled shared-memory tiles; attention is 1-3 % of the step's FLOPs at these lengths
+// (SURVEY §8(d)), the tcgen05 GEMMs carry the rest.
+//   forward : O, LSE
+//   backward: delta = rowsum(dO*O); dK,dV kernel (one CTA per key block, loops query blocks, S^T formulation);
+//             dQ kernel (one CTA per query block, loops key blocks). No atomics, no fp32 dQ buffer.
+#include "common.h"
+#include "ptx.cuh"
+
+using namespace nbest;
+
+namespace {
+
+constexpr int D = 64;        // head dim
+constexpr int BLK = 64;      // query / key block
+constexpr int kThreads = 128;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int chunk) {
+  return base + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+
+// 64 x 64 bf16 tile, global (row pitch ld elements) -> swizzled smem, rows >= rows_valid zero-filled.
+__device__ __forceinline__ void load_tile(uint32_t sbase, const __nv_bfloat16* g, int64_t ld, int rows_valid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = threadIdx.x + kThreads * i;
+    const int row = idx >> 3, chunk = idx & 7;
+    const bool ok = row < rows_valid;
+    cp_async_16(tile_addr(sbase, row, chunk), g + (ok ? (int64_t)row * ld : 0) + chunk * 8, ok);
+  }
+}
+
+// A fragment (16 rows x 16 k) of a row-major [row][k] tile.
+__device__ __forceinline__ void lda(uint32_t (&a)[4], uint32_t sbase, int row0, int kk, int lane) {
+  ldmatrix_x4(a, tile_addr(sbase, row0 + (lane & 15), 2 * kk + (lane >> 4)));
+}
+// B fragments for two n8 tiles from a [n][k] row-major tile (B = tile^T): b[0],b[1] -> n-tile n0/8, b[2],b[3] -> next.
+__device__ __forceinline__ void ldb_nk(uint32_t (&b)[4], uint32_t sbase, int n0, int kk, int lane) {
+  ldmatrix_x4(b, tile_addr(sbase, n0 + (lane & 7) + ((lane >> 4) << 3), 2 * kk + ((lane >> 3) & 1)));
+}
+// B fragments for two n8 tiles from a [k][n] row-major tile: k rows k0..k0+15, n chunks nc, nc+1.
+__device__ __forceinline__ void ldb_kn(uint32_t (&b)[4], uint32_t sbase, int k0, int nc, int lane) {
+  ldmatrix_x4_trans(b, tile_addr(sbase, k0 + (lane & 7) + (((lane >> 3) & 1) << 3), nc + (lane >> 4)));
+}
+
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// acc[16 x 64] (8 n-tiles) = A(16 x 64 from tile rows row0..) * B^T where B tile is [n][k] (64 x 64).
+__device__ __forceinline__ void mma_a_tile_b_nk(float (&acc)[8][4], uint32_t sA, int row0, uint32_t sB, int lane) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[4];
+    lda(a, sA, row0, kk, lane);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ldb_nk(b, sB, np * 16, kk, lane);
+      mma_bf16_16816(acc[2 * np], a, b[0], b[1]);
+      mma_bf16_16816(acc[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+}
+// acc[16 x 64] += P(16 x 64, fp32 accumulator layout, converted to bf16 A fragments) * B where B tile is [k][n].
+__device__ __forceinline__ void mma_p_b_kn(float (&acc)[8][4], const float (&p)[8][4], uint32_t sB, int lane) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[4];
+    a[0] = pack_bf16x2(p[2 * kk][0], p[2 * kk][1]);
+    a[1] = pack_bf16x2(p[2 * kk][2], p[2 * kk][3]);
+    a[2] = pack_bf16x2(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+    a[3] = pack_bf16x2(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {
+      uint32_t b[4];
+      ldb_kn(b, sB, kk * 16, dp * 2, lane);
+      mma_bf16_16816(acc[2 * dp], a, b[0], b[1]);
+      mma_bf16_16816(acc[2 * dp + 1], a, b[2], b[3]);
+    }
+  }
+}
+
+__device__ __forceinline__ void zero_acc(float (&a)[8][4]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
+}
+
+// dropout index of attention probability (head h, query token tq (global), key j inside the sequence)
+__device__ __forceinline__ uint32_t pidx(int h, int T, int tq, int j) { return ((uint32_t)h * (uint32_t)T + (uint32_t)tq) * 512u + (uint32_t)j; }
+
+// ------------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(kThreads)
+attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu, const uint8_t* __restrict__ key_valid,
+                int heads, int T, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, float scale, uint32_t thr,
+                float rscale, uint32_t seed) {
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int s0 = cu[b], L = cu[b + 1] - s0;
+  const int q0 = qb * BLK;
+  if (q0 >= L) return;
+  __shared__ __align__(128) __nv_bfloat16 sQ[BLK * D], sK[BLK * D], sV[BLK * D];
+  __shared__ uint8_t sValid[BLK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t ld = 3 * heads * D;
+  const int hd = heads * D;
+  const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV);
+  load_tile(uQ, qkv + (int64_t)(s0 + q0) * ld + h * D, ld, L - q0);
+
+  float o[8][4];
+  zero_acc(o);
+  float m_i[2] = {-INFINITY, -INFINITY}, l_i[2] = {0.f, 0.f};
+  const float sl2 = scale * kLog2e;
+  uint32_t qf[4][4];
+  const int nkb = (L + BLK - 1) / BLK;
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int k0 = kb * BLK;
+    load_tile(uK, qkv + (int64_t)(s0 + k0) * ld + hd + h * D, ld, L - k0);
+    load_tile(uV, qkv + (int64_t)(s0 + k0) * ld + 2 * hd + h * D, ld, L - k0);
+    cp_async_commit();
+    if (threadIdx.x < BLK) {
+      const int j = k0 + threadIdx.x;
+      sValid[threadIdx.x] = (j < L) && (key_valid == nullptr || key_valid[s0 + j] != 0);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    if (kb == 0) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) lda(qf[kk], uQ, warp * 16, kk, lane);
+    }
+    float s[8][4];
+    zero_acc(s);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t bf[4];
+        ldb_nk(bf, uK, np * 16, kk, lane);
+        mma_bf16_16816(s[2 * np], qf[kk], bf[0], bf[1]);
+        mma_bf16_16816(s[2 * np + 1], qf[kk], bf[2], bf[3]);
+      }
+    }
+    // mask
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = nt * 8 + (lane & 3) * 2;
+      const bool v0 = sValid[c], v1 = sValid[c + 1];
+      if (!v0) s[nt][0] = s[nt][2] = -INFINITY;
+      if (!v1) s[nt][1] = s[nt][3] = -INFINITY;
+    }
+    // online softmax (rows r=0: lane/4, r=1: lane/4+8)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mx = fmaxf(mx, fmaxf(s[nt][2 * r], s[nt][2 * r + 1]));
+      mx = quad_max(mx);
+      const float m_new = fmaxf(m_i[r], mx);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float corr = exp2f((m_i[r] - m_use) * sl2);
+      m_i[r] = m_new;
+      float rs = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float p0 = exp2f((s[nt][2 * r] - m_use) * sl2), p1 = exp2f((s[nt][2 * r + 1] - m_use) * sl2);
+        s[nt][2 * r] = p0;
+        s[nt][2 * r + 1] = p1;
+        rs += p0 + p1;
+        o[nt][2 * r] *= corr;
+        o[nt][2 * r + 1] *= corr;
+      }
+      l_i[r] = l_i[r] * corr + rs;
+    }
+    if (thr) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int tq = s0 + q0 + warp * 16 + (lane >> 2) + ((e >> 1) << 3);
+          const int j = k0 + nt * 8 + (lane & 3) * 2 + (e & 1);
+          s[nt][e] = dropout_keep(seed, pidx(h, T, tq, j), thr) ? s[nt][e] * rscale : 0.f;
+        }
+    }
+    mma_p_b_kn(o, s, uV, lane);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const float l = quad_sum(l_i[r]);
+    const int row = q0 + warp * 16 + (lane >> 2) + 8 * r;
+    if (row < L) {
+      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      __nv_bfloat16* orow = out + (int64_t)(s0 + row) * hd + h * D + (lane & 3) * 2;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+        *reinterpret_cast<uint32_t*>(orow + nt * 8) = pack_bf16x2(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
+      if ((lane & 3) == 0) lse[(int64_t)h * T + s0 + row] = (l > 0.f) ? m_i[r] * scale + logf(l) : 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: delta
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, int T,
+                                  int heads, float* __restrict__ delta) {
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const int lane = threadIdx.x & 31;
+  const int hd = heads * D;
+  for (int c = lane * 8; c < hd; c += 256) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + (int64_t)t * hd + c));
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(dout + (int64_t)t * hd + c));
+    float s = bf16lo(a.x) * bf16lo(g.x) + bf16hi(a.x) * bf16hi(g.x) + bf16lo(a.y) * bf16lo(g.y) + bf16hi(a.y) * bf16hi(g.y) +
+              bf16lo(a.z) * bf16lo(g.z) + bf16hi(a.z) * bf16hi(g.z) + bf16lo(a.w) * bf16lo(g.w) + bf16hi(a.w) * bf16hi(g.w);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if ((lane & 7) == 0) delta[(int64_t)(c >> 6) * T + t] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dK, dV
+// One CTA per (key block, head, sequence); warp w owns keys [16w, 16w+16) of the block. Works on S^T = K Q^T so that
+// P^T / dS^T come out of the MMA already in A-fragment layout for the dV = P^T dO and dK = dS^T Q products.
+__global__ void __launch_bounds__(kThreads)
+attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
+                     const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
+                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
+                     float scale, uint32_t thr, float rscale, uint32_t seed) {
+  const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int s0 = cu[b], L = cu[b + 1] - s0;
+  const int k0 = kb * BLK;
+  if (k0 >= L) return;
+  __shared__ __align__(128) __nv_bfloat16 sK[BLK * D], sV[BLK * D], sQ[BLK * D], sdO[BLK * D];
+  __shared__ float sLse[BLK], sDelta[BLK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t ld = 3 * heads * D;
+  const int hd = heads * D;
+  const uint32_t uK = smem_u32(sK), uV = smem_u32(sV), uQ = smem_u32(sQ), uO = smem_u32(sdO);
+  load_tile(uK, qkv + (int64_t)(s0 + k0) * ld + hd + h * D, ld, L - k0);
+  load_tile(uV, qkv + (int64_t)(s0 + k0) * ld + 2 * hd + h * D, ld, L - k0);
+  // validity of this thread's two key rows (S^T rows: lane/4 and lane/4+8 inside the warp's 16 keys)
+  bool kval[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int j = k0 + warp * 16 + (lane >> 2) + 8 * r;
+    kval[r] = (j < L) && (key_valid == nullptr || key_valid[s0 + j] != 0);
+  }
+  float dk[8][4], dv[8][4];
+  zero_acc(dk);
+  zero_acc(dv);
+  const float sl2 = scale * kLog2e;
+  const int nqb = (L + BLK - 1) / BLK;
+  for (int qb = 0; qb < nqb; ++qb) {
+    const int q0 = qb * BLK;
+    load_tile(uQ, qkv + (int64_t)(s0 + q0) * ld + h * D, ld, L - q0);
+    load_tile(uO, dout + (int64_t)(s0 + q0) * hd + h * D, hd, L - q0);
+    cp_async_commit();
+    if (threadIdx.x < BLK) {
+      const int q = q0 + threadIdx.x;
+      sLse[threadIdx.x] = q < L ? lse[(int64_t)h * T + s0 + q] * kLog2e : INFINITY;  // +inf -> P = 0 for padded queries
+      sDelta[threadIdx.x] = q < L ? delta[(int64_t)h * T + s0 + q] : 0.f;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    float st[8][4], dpt[8][4];
+    zero_acc(st);
+    zero_acc(dpt);
+    mma_a_tile_b_nk(st, uK, warp * 16, uQ, lane);    // S^T  [16 keys x 64 queries]
+    mma_a_tile_b_nk(dpt, uV, warp * 16, uO, lane);   // dP^T [16 keys x 64 queries]
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int qc = nt * 8 + (lane & 3) * 2 + (e & 1);
+        const int r = e >> 1;
+        float p = kval[r] ? exp2f(st[nt][e] * sl2 - sLse[qc]) : 0.f;
+        float dp = dpt[nt][e];
+        float pd = p;
+        if (thr) {
+          const int tq = s0 + q0 + qc;
+          const int j = k0 + warp * 16 + (lane >> 2) + 8 * r;
+          const bool keep = dropout_keep(seed, pidx(h, T, tq, j), thr);
+          pd = keep ? p * rscale : 0.f;
+          dp = keep ? dp * rscale : 0.f;
+        }
+        st[nt][e] = pd;                               // dropped P^T  -> dV
+        dpt[nt][e] = p * (dp - sDelta[qc]);           // dS^T         -> dK
+      }
+    mma_p_b_kn(dv, st, uO, lane);    // dV += P^T dO   (B = dO [q][d])
+    mma_p_b_kn(dk, dpt, uQ, lane);   // dK += dS^T Q   (B = Q  [q][d])
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = k0 + warp * 16 + (lane >> 2) + 8 * r;
+    if (row < L) {
+      __nv_bfloat16* krow = dqkv + (int64_t)(s0 + row) * ld + hd + h * D + (lane & 3) * 2;
+      __nv_bfloat16* vrow = krow + hd;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        *reinterpret_cast<uint32_t*>(krow + nt * 8) = pack_bf16x2(dk[nt][2 * r] * scale, dk[nt][2 * r + 1] * scale);
+        *reinterpret_cast<uint32_t*>(vrow + nt * 8) = pack_bf16x2(dv[nt][2 * r], dv[nt][2 * r + 1]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dQ
+__global__ void __launch_bounds__(kThreads)
+attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
+                   const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
+                   const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
+                   float scale, uint32_t thr, float rscale, uint32_t seed) {
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int s0 = cu[b], L = cu[b + 1] - s0;
+  const int q0 = qb * BLK;
+  if (q0 >= L) return;
+  __shared__ __align__(128) __nv_bfloat16 sQ[BLK * D], sdO[BLK * D], sK[BLK * D], sV[BLK * D];
+  __shared__ uint8_t sValid[BLK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t ld = 3 * heads * D;
+  const int hd = heads * D;
+  const uint32_t uK = smem_u32(sK), uV = smem_u32(sV), uQ = smem_u32(sQ), uO = smem_u32(sdO);
+  load_tile(uQ, qkv + (int64_t)(s0 + q0) * ld + h * D, ld, L - q0);
+  load_tile(uO, dout + (int64_t)(s0 + q0) * hd + h * D, hd, L - q0);
+  float lse2[2], dl[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int q = q0 + warp * 16 + (lane >> 2) + 8 * r;
+    lse2[r] = q < L ? lse[(int64_t)h * T + s0 + q] * kLog2e : INFINITY;
+    dl[r] = q < L ? delta[(int64_t)h * T + s0 + q] : 0.f;
+  }
+  float dq[8][4];
+  zero_acc(dq);
+  const float sl2 = scale * kLog2e;
+  const int nkb = (L + BLK - 1) / BLK;
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int k0 = kb * BLK;
+    load_tile(uK, qkv + (int64_t)(s0 + k0) * ld + hd + h * D, ld, L - k0);
+    load_tile(uV, qkv + (int64_t)(s0 + k0) * ld + 2 * hd + h * D, ld, L - k0);
+    cp_async_commit();
+    if (threadIdx.x < BLK) {
+      const int j = k0 + threadIdx.x;
+      sValid[threadIdx.x] = (j < L) && (key_valid == nullptr || key_valid[s0 + j] != 0);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    float s[8][4], dp[8][4];
+    zero_acc(s);
+    zero_acc(dp);
+    mma_a_tile_b_nk(s, uQ, warp * 16, uK, lane);     // S  [16 q x 64 keys]
+    mma_a_tile_b_nk(dp, uO, warp * 16, uV, lane);    // dP [16 q x 64 keys] = dO V^T
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kc = nt * 8 + (lane & 3) * 2 + (e & 1);
+        const int r = e >> 1;
+        const float p = sValid[kc] ? exp2f(s[nt][e] * sl2 - lse2[r]) : 0.f;
+        float d = dp[nt][e];
+        if (thr) {
+          const int tq = s0 + q0 + warp * 16 + (lane >> 2) + 8 * r;
+          d = dropout_keep(seed, pidx(h, T, tq, k0 + kc), thr) ? d * rscale : 0.f;
+        }
+        s[nt][e] = p * (d - dl[r]);                   // dS
+      }
+    mma_p_b_kn(dq, s, uK, lane);                      // dQ += dS K   (B = K [key][d])
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = q0 + warp * 16 + (lane >> 2) + 8 * r;
+    if (row < L) {
+      __nv_bfloat16* qrow = dqkv + (int64_t)(s0 + row) * ld + h * D + (lane & 3) * 2;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+        *reinterpret_cast<uint32_t*>(qrow + nt * 8) = pack_bf16x2(dq[nt][2 * r] * scale, dq[nt][2 * r + 1] * scale);
+    }
+  }
+}
+
+inline uint32_t drop_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  return p <= 0.f ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+}
+
+}  // namespace
+
+extern "C" int nbest_attn_varlen_fwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens,
+                                     const uint8_t* key_valid, int B, int max_len, int heads, int T, void* out_bf16,
+                                     float* lse, float p_drop, uint32_t seed, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, qkv_bf16 && cu_seqlens && out_bf16 && lse, "null pointer");
+  NBEST_CHECK_ARG(ctx, B > 0 && heads > 0 && max_len > 0 && max_len <= 512, "need 0 < max_len <= 512 (BERT position limit)");
+  NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
+  NBEST_CHECK_ARG(ctx, B <= 65535, "B too large for one launch");
+  const dim3 grid((max_len + BLK - 1) / BLK, heads, B);
+  attn_fwd_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), cu_seqlens, key_valid, heads, T,
+      reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, 0.125f, drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
+extern "C" int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens,
+                                     const uint8_t* key_valid, int B, int max_len, int heads, int T, const void* out_bf16,
+                                     const void* dout_bf16, const float* lse, void* dqkv_bf16, float* delta_ws, float p_drop,
+                                     uint32_t seed, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, qkv_bf16 && cu_seqlens && out_bf16 && dout_bf16 && lse && dqkv_bf16 && delta_ws, "null pointer");
+  NBEST_CHECK_ARG(ctx, B > 0 && heads > 0 && max_len > 0 && max_len <= 512, "need 0 < max_len <= 512 (BERT position limit)");
+  NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
+  NBEST_CHECK_ARG(ctx, B <= 65535, "B too large for one launch");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const auto* q = reinterpret_cast<const __nv_bfloat16*>(qkv_bf16);
+  const auto* o = reinterpret_cast<const __nv_bfloat16*>(out_bf16);
+  const auto* g = reinterpret_cast<const __nv_bfloat16*>(dout_bf16);
+  auto* dq = reinterpret_cast<__nv_bfloat16*>(dqkv_bf16);
+  if (T > 0) {
+    attn_delta_kernel<<<(T + 7) / 8, 256, 0, s>>>(o, g, T, heads, delta_ws);
+    NBEST_CHECK_LAUNCH(ctx);
+  }
+  const dim3 grid((max_len + BLK - 1) / BLK, heads, B);
+  const uint32_t thr = drop_threshold(p_drop);
+  const float rscale = 1.0f / (1.0f - p_drop);
+  attn_bwd_dkdv_kernel<<<grid, kThreads, 0, s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f, thr, rscale, seed);
+  NBEST_CHECK_LAUNCH(ctx);
+  attn_bwd_dq_kernel<<<grid, kThreads, 0, s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f, thr, rscale, seed);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}

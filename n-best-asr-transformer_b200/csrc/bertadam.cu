@@ -1,0 +1,113 @@
+// Fused multi-tensor BertAdam over one flat fp32 parameter buffer.
+//
+// Reference: BertAdam.step (models/optimization.py:237-302) run over 221 one-tensor param groups
+// (n_best_asr_bert.py:535-550): per tensor clip_grad_norm_(p, 1.0) (:270-271), m/v moments (:275-276),
+// update = m / (sqrt(v) + e) + wd * p (:277-287), p -= lr * schedule(step/t_total) * update (:289-293), no bias
+// correction. The reference launches ~14 kernels per tensor (~3 k per step); here it is two launches per step:
+//   pass 1: per-tensor sum of squares of the gradient                       (reads g:           4 B / param)
+//   pass 2: clip + moments + decay + update (+ bf16 working copy refresh)   (reads p,g,m,v, writes p,m,v[,bf16]: 28-30 B)
+#include "common.h"
+#include "ptx.cuh"
+
+using namespace nbest;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads)
+adam_norm_kernel(const float* __restrict__ g, const nbest_adam_tensor* __restrict__ tensors, const int32_t* __restrict__ chunks,
+                 float* __restrict__ norms) {
+  const int ti = chunks[3 * blockIdx.x], start = chunks[3 * blockIdx.x + 1], len = chunks[3 * blockIdx.x + 2];
+  const float* gp = g + tensors[ti].offset + start;   // offset and start are multiples of 4 elements
+  float acc = 0.f;
+  const int n4 = len >> 2;
+  for (int i = threadIdx.x; i < n4; i += kThreads) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(gp) + i);
+    acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  for (int i = (n4 << 2) + threadIdx.x; i < len; i += kThreads) acc += gp[i] * gp[i];
+  acc = warp_sum(acc);
+  __shared__ float sh[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(norms + ti, v);
+  }
+}
+
+__device__ __forceinline__ float adam_elem(float& p, float g, float& m, float& v, float coef, float b1, float b2, float eps,
+                                           float wd, float lr_t) {
+  g *= coef;
+  m = m * b1 + (1.0f - b1) * g;
+  v = v * b2 + (1.0f - b2) * g * g;
+  float upd = m / (sqrtf(v) + eps);
+  if (wd > 0.f) upd += wd * p;
+  p -= lr_t * upd;
+  return p;
+}
+
+__global__ void __launch_bounds__(kThreads)
+adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                   __nv_bfloat16* __restrict__ pb, const nbest_adam_tensor* __restrict__ tensors,
+                   const int32_t* __restrict__ chunks, const float* __restrict__ norms, double sched, float b1, float b2,
+                   float eps, float max_grad_norm) {
+  const int ti = chunks[3 * blockIdx.x], start = chunks[3 * blockIdx.x + 1], len = chunks[3 * blockIdx.x + 2];
+  const nbest_adam_tensor t = tensors[ti];
+  const int64_t base = t.offset + start;
+  float coef = 1.0f;
+  if (max_grad_norm > 0.f) {
+    const float nrm = sqrtf(norms[ti]);
+    coef = fminf(max_grad_norm / (nrm + 1e-6f), 1.0f);   // clip_grad_norm_: clamp(max_norm / (norm + 1e-6), max=1)
+  }
+  const float lr_t = (float)(t.lr * sched);
+  const float wd = t.weight_decay;
+  const int n4 = len >> 2;
+  for (int i = threadIdx.x; i < n4; i += kThreads) {
+    float4 pv = reinterpret_cast<float4*>(p + base)[i];
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g + base) + i);
+    float4 mv = reinterpret_cast<float4*>(m + base)[i];
+    float4 vv = reinterpret_cast<float4*>(v + base)[i];
+    adam_elem(pv.x, gv.x, mv.x, vv.x, coef, b1, b2, eps, wd, lr_t);
+    adam_elem(pv.y, gv.y, mv.y, vv.y, coef, b1, b2, eps, wd, lr_t);
+    adam_elem(pv.z, gv.z, mv.z, vv.z, coef, b1, b2, eps, wd, lr_t);
+    adam_elem(pv.w, gv.w, mv.w, vv.w, coef, b1, b2, eps, wd, lr_t);
+    reinterpret_cast<float4*>(p + base)[i] = pv;
+    reinterpret_cast<float4*>(m + base)[i] = mv;
+    reinterpret_cast<float4*>(v + base)[i] = vv;
+    if (pb) *reinterpret_cast<uint2*>(pb + base + 4 * i) = make_uint2(pack_bf16x2(pv.x, pv.y), pack_bf16x2(pv.z, pv.w));
+  }
+  for (int i = (n4 << 2) + threadIdx.x; i < len; i += kThreads) {
+    float pv = p[base + i], mv = m[base + i], vv = v[base + i];
+    adam_elem(pv, g[base + i], mv, vv, coef, b1, b2, eps, wd, lr_t);
+    p[base + i] = pv;
+    m[base + i] = mv;
+    v[base + i] = vv;
+    if (pb) pb[base + i] = __float2bfloat16_rn(pv);
+  }
+}
+
+}  // namespace
+
+extern "C" int nbest_bertadam_step(nbest_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16,
+                                   const nbest_adam_tensor* tensors, int n_tensors, const int32_t* chunks, int n_chunks,
+                                   float* norms_ws, double sched, float b1, float b2, float eps, float max_grad_norm,
+                                   void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, p && g && m && v && tensors && chunks && norms_ws, "null pointer");
+  NBEST_CHECK_ARG(ctx, n_tensors > 0 && n_chunks > 0, "empty tensor table");
+  NBEST_CHECK_ARG(ctx, ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                         reinterpret_cast<uintptr_t>(v)) & 15) == 0, "flat buffers must be 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (max_grad_norm > 0.f) {
+    NBEST_CHECK_CUDA(ctx, cudaMemsetAsync(norms_ws, 0, sizeof(float) * n_tensors, s));
+    adam_norm_kernel<<<n_chunks, kThreads, 0, s>>>(g, tensors, chunks, norms_ws);
+    NBEST_CHECK_LAUNCH(ctx);
+  }
+  adam_update_kernel<<<n_chunks, kThreads, 0, s>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), tensors, chunks,
+                                                    norms_ws, sched, b1, b2, eps, max_grad_norm);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}

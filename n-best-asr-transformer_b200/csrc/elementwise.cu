@@ -1,0 +1,491 @@
+// Memory-bound kernels of the packed encoder: batch packing, embedding gather + LayerNorm, LayerNorm fwd/bwd,
+// column sums and the fp32 -> bf16 weight refresh. All are one-warp-per-token (hidden = 768 = 32 lanes x 6 x float4),
+// 8/16-byte vector accesses, warp-shuffle reductions, fp32 statistics.
+//
+// Reference counterparts: utils/bert_xlnet_inputs.py:91-102 + models/model.py:43 (packing / key mask),
+// transformers modeling_bert.py:102-112 (BertEmbeddings), :294-298 and :352-356 (residual LayerNorms).
+#include "common.h"
+#include "ptx.cuh"
+
+using namespace nbest;
+
+namespace {
+
+constexpr int H = 768;          // models/model.py:30 hard-codes fea_dim = 768
+constexpr int VPL = H / 128;    // float4 vectors per lane (6)
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 bf16x4_to_f4(uint2 u) { return make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y)); }
+__device__ __forceinline__ uint2 f4_to_bf16x4(float4 v) { return make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)); }
+static inline uint32_t drop_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  return p <= 0.f ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+}
+
+// ------------------------------------------------------------------------------------------------ packing
+__global__ void pack_lens_kernel(const int64_t* __restrict__ ids, int B, int S, int32_t* __restrict__ lens) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const int lane = threadIdx.x & 31;
+  int last = 0;
+  for (int j = lane; j < S; j += 32)
+    if (ids[(int64_t)row * S + j] > 0) last = j + 1;
+  for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  if (lane == 0) lens[row] = last;
+}
+
+__global__ void pack_scan_kernel(const int32_t* __restrict__ lens, int B, int32_t* __restrict__ cu) {
+  __shared__ int32_t sh[1024];
+  __shared__ int32_t carry;
+  if (threadIdx.x == 0) {
+    carry = 0;
+    cu[0] = 0;
+  }
+  __syncthreads();
+  for (int base = 0; base < B; base += 1024) {
+    const int i = base + threadIdx.x;
+    int v = i < B ? lens[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (i < B) cu[i + 1] = carry + sh[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) carry += sh[1023];
+    __syncthreads();
+  }
+}
+
+__global__ void pack_scatter_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ seg_ids, int B, int S,
+                                    int pos_mode, const int32_t* __restrict__ cu, int32_t* __restrict__ tokens,
+                                    uint8_t* __restrict__ seg, int32_t* __restrict__ pos, int32_t* __restrict__ seq_of,
+                                    uint8_t* __restrict__ key_valid) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const int lane = threadIdx.x & 31;
+  const int t0 = cu[row], L = cu[row + 1] - cu[row];
+  int carry = 0;
+  for (int c = 0; c < L; c += 32) {
+    const int j = c + lane;
+    const bool in = j < L;
+    const int64_t id = in ? ids[(int64_t)row * S + j] : 1;
+    const bool nonpad = in && id != 1;
+    const uint32_t m = __ballot_sync(0xffffffffu, nonpad);
+    if (in) {
+      const int t = t0 + j;
+      tokens[t] = (int32_t)id;
+      seg[t] = seg_ids ? (uint8_t)seg_ids[(int64_t)row * S + j] : (uint8_t)0;
+      seq_of[t] = row;
+      key_valid[t] = id > 0 ? 1 : 0;
+      if (pos_mode == 1) {
+        const int incl = carry + __popc(m & (0xffffffffu >> (31 - lane)));
+        pos[t] = nonpad ? incl + 1 : 1;
+      } else {
+        pos[t] = j;
+      }
+    }
+    carry += __popc(m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm core
+struct RowStats {
+  float mean, rstd;
+};
+
+__device__ __forceinline__ RowStats row_stats(const float4 (&x)[VPL], float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+  const float mean = warp_sum(s) * (1.0f / H);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = warp_sum(q) * (1.0f / H);
+  return RowStats{mean, rsqrtf(var + eps)};
+}
+
+// y = dropout(LN(x)) for one row held in registers; writes bf16.
+__device__ __forceinline__ void ln_apply_store(const float4 (&x)[VPL], RowStats st, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, __nv_bfloat16* __restrict__ yrow, int lane,
+                                               uint32_t thr, float scale, uint32_t seed, uint32_t row_base) {
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = 4 * (lane + 32 * i);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 y;
+    y.x = (x[i].x - st.mean) * st.rstd * g.x + b.x;
+    y.y = (x[i].y - st.mean) * st.rstd * g.y + b.y;
+    y.z = (x[i].z - st.mean) * st.rstd * g.z + b.z;
+    y.w = (x[i].w - st.mean) * st.rstd * g.w + b.w;
+    if (thr) {
+      y.x = dropout_keep(seed, row_base + c + 0, thr) ? y.x * scale : 0.f;
+      y.y = dropout_keep(seed, row_base + c + 1, thr) ? y.y * scale : 0.f;
+      y.z = dropout_keep(seed, row_base + c + 2, thr) ? y.z * scale : 0.f;
+      y.w = dropout_keep(seed, row_base + c + 3, thr) ? y.w * scale : 0.f;
+    }
+    *reinterpret_cast<uint2*>(yrow + c) = f4_to_bf16x4(y);
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+embed_ln_fwd_kernel(const int32_t* __restrict__ tokens, const uint8_t* __restrict__ seg, const int32_t* __restrict__ pos,
+                    int T, const float* __restrict__ word, const float* __restrict__ posemb, const float* __restrict__ type,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                    __nv_bfloat16* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, uint32_t thr,
+                    float scale, uint32_t seed) {
+  const int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const int lane = threadIdx.x & 31;
+  const float* w = word + (int64_t)tokens[t] * H;
+  const float* p = posemb + (int64_t)pos[t] * H;
+  const float* ty = type + (int64_t)seg[t] * H;
+  float4 x[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = 4 * (lane + 32 * i);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + c));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(ty + c));
+    x[i] = make_float4(a.x + d.x + b.x, a.y + d.y + b.y, a.z + d.z + b.z, a.w + d.w + b.w);  // word + type + pos (HF order)
+  }
+  const RowStats st = row_stats(x, eps);
+  if (lane == 0) {
+    mean[t] = st.mean;
+    rstd[t] = st.rstd;
+  }
+  ln_apply_store(x, st, gamma, beta, y + (int64_t)t * H, lane, thr, scale, seed, (uint32_t)t * H);
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ln_fwd_kernel(const __nv_bfloat16* __restrict__ xin, const float* __restrict__ gamma, const float* __restrict__ beta,
+              float eps, int T, __nv_bfloat16* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+  const int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const int lane = threadIdx.x & 31;
+  const __nv_bfloat16* xr = xin + (int64_t)t * H;
+  float4 x[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) x[i] = bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(xr + 4 * (lane + 32 * i))));
+  const RowStats st = row_stats(x, eps);
+  if (lane == 0) {
+    if (mean) mean[t] = st.mean;
+    if (rstd) rstd[t] = st.rstd;
+  }
+  ln_apply_store(x, st, gamma, beta, y + (int64_t)t * H, lane, 0u, 1.f, 0u, 0u);
+}
+
+// Block-level reduction of per-warp column partials (VPL float4 per lane) followed by one atomic per column per block.
+__device__ __forceinline__ void block_reduce_cols_atomic(float4 (&acc)[VPL], float* __restrict__ out, float* sh /*[warps][H]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) *reinterpret_cast<float4*>(sh + warp * H + 4 * (lane + 32 * i)) = acc[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; ++w) s += sh[w * H + c];
+    atomicAdd(out + c, s);
+  }
+}
+
+__device__ __forceinline__ void f4_acc(float4& a, const float4& b) {
+  a.x += b.x;
+  a.y += b.y;
+  a.z += b.z;
+  a.w += b.w;
+}
+
+// LayerNorm backward for a row in registers: returns dx (fp32) in `g` (overwrites), accumulates dgamma/dbeta partials.
+__device__ __forceinline__ void ln_bwd_row(const float4 (&xhat)[VPL], float4 (&dy)[VPL], float rstd_v,
+                                           const float* __restrict__ gamma, int lane, float4 (&dgam)[VPL],
+                                           float4 (&dbet)[VPL]) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + 4 * (lane + 32 * i)));
+    dgam[i].x += dy[i].x * xhat[i].x;
+    dgam[i].y += dy[i].y * xhat[i].y;
+    dgam[i].z += dy[i].z * xhat[i].z;
+    dgam[i].w += dy[i].w * xhat[i].w;
+    f4_acc(dbet[i], dy[i]);
+    dy[i].x *= gm.x;
+    dy[i].y *= gm.y;
+    dy[i].z *= gm.z;
+    dy[i].w *= gm.w;
+    s1 += (dy[i].x + dy[i].y) + (dy[i].z + dy[i].w);
+    s2 += (dy[i].x * xhat[i].x + dy[i].y * xhat[i].y) + (dy[i].z * xhat[i].z + dy[i].w * xhat[i].w);
+  }
+  const float c1 = warp_sum(s1) * (1.0f / H), c2 = warp_sum(s2) * (1.0f / H);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    dy[i].x = rstd_v * (dy[i].x - c1 - xhat[i].x * c2);
+    dy[i].y = rstd_v * (dy[i].y - c1 - xhat[i].y * c2);
+    dy[i].z = rstd_v * (dy[i].z - c1 - xhat[i].z * c2);
+    dy[i].w = rstd_v * (dy[i].w - c1 - xhat[i].w * c2);
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ dyin, const __nv_bfloat16* __restrict__ xin, const float* __restrict__ mean,
+              const float* __restrict__ rstd, const float* __restrict__ gamma, int T, __nv_bfloat16* __restrict__ dx,
+              __nv_bfloat16* __restrict__ dxm, uint32_t thr, float scale, uint32_t seed, float* __restrict__ dgamma,
+              float* __restrict__ dbeta, float* __restrict__ dbias) {
+  __shared__ float sh[kWarpsPerBlock * H];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 dgam[VPL], dbet[VPL], dbia[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) dgam[i] = dbet[i] = dbia[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = blockIdx.x * kWarpsPerBlock + warp; t < T; t += gridDim.x * kWarpsPerBlock) {
+    const float mu = mean[t], rs = rstd[t];
+    float4 xhat[VPL], dy[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      const float4 xv = bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(xin + (int64_t)t * H + c)));
+      xhat[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      dy[i] = bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(dyin + (int64_t)t * H + c)));
+    }
+    ln_bwd_row(xhat, dy, rs, gamma, lane, dgam, dbet);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      *reinterpret_cast<uint2*>(dx + (int64_t)t * H + c) = f4_to_bf16x4(dy[i]);
+      float4 m = dy[i];
+      if (dxm != nullptr) {
+        const uint32_t base = (uint32_t)t * H + c;
+        m.x = dropout_keep(seed, base + 0, thr) ? m.x * scale : 0.f;
+        m.y = dropout_keep(seed, base + 1, thr) ? m.y * scale : 0.f;
+        m.z = dropout_keep(seed, base + 2, thr) ? m.z * scale : 0.f;
+        m.w = dropout_keep(seed, base + 3, thr) ? m.w * scale : 0.f;
+        *reinterpret_cast<uint2*>(dxm + (int64_t)t * H + c) = f4_to_bf16x4(m);
+      }
+      f4_acc(dbia[i], m);
+    }
+  }
+  block_reduce_cols_atomic(dgam, dgamma, sh);
+  block_reduce_cols_atomic(dbet, dbeta, sh);
+  if (dbias != nullptr) block_reduce_cols_atomic(dbia, dbias, sh);
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+embed_ln_bwd_kernel(const int32_t* __restrict__ tokens, const uint8_t* __restrict__ seg, const int32_t* __restrict__ pos,
+                    int T, const float* __restrict__ word, const float* __restrict__ posemb, const float* __restrict__ type,
+                    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const __nv_bfloat16* __restrict__ dyin, uint32_t thr, float scale, uint32_t seed,
+                    float* __restrict__ dword, float* __restrict__ dpos, float* __restrict__ dtype,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, int word_pad_row, int pos_pad_row) {
+  __shared__ float sh[kWarpsPerBlock * H];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 dgam[VPL], dbet[VPL], dty0[VPL], dty1[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) dgam[i] = dbet[i] = dty0[i] = dty1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool any1 = false;
+  for (int t = blockIdx.x * kWarpsPerBlock + warp; t < T; t += gridDim.x * kWarpsPerBlock) {
+    const int tok = tokens[t], ps = pos[t], sg = seg[t];
+    const float mu = mean[t], rs = rstd[t];
+    const float* w = word + (int64_t)tok * H;
+    const float* p = posemb + (int64_t)ps * H;
+    const float* ty = type + (int64_t)sg * H;
+    float4 xhat[VPL], dy[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      const float4 a = __ldg(reinterpret_cast<const float4*>(w + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p + c));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(ty + c));
+      xhat[i] = make_float4((a.x + d.x + b.x - mu) * rs, (a.y + d.y + b.y - mu) * rs, (a.z + d.z + b.z - mu) * rs,
+                            (a.w + d.w + b.w - mu) * rs);
+      dy[i] = bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(dyin + (int64_t)t * H + c)));
+      if (thr) {
+        const uint32_t base = (uint32_t)t * H + c;
+        dy[i].x = dropout_keep(seed, base + 0, thr) ? dy[i].x * scale : 0.f;
+        dy[i].y = dropout_keep(seed, base + 1, thr) ? dy[i].y * scale : 0.f;
+        dy[i].z = dropout_keep(seed, base + 2, thr) ? dy[i].z * scale : 0.f;
+        dy[i].w = dropout_keep(seed, base + 3, thr) ? dy[i].w * scale : 0.f;
+      }
+    }
+    ln_bwd_row(xhat, dy, rs, gamma, lane, dgam, dbet);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      if (tok != word_pad_row) red_add_v4(dword + (int64_t)tok * H + c, dy[i]);
+      if (ps != pos_pad_row) red_add_v4(dpos + (int64_t)ps * H + c, dy[i]);
+      if (sg == 0) {
+        f4_acc(dty0[i], dy[i]);
+      } else if (sg == 1) {
+        f4_acc(dty1[i], dy[i]);
+        any1 = true;
+      } else {
+        red_add_v4(dtype + (int64_t)sg * H + c, dy[i]);
+      }
+    }
+  }
+  block_reduce_cols_atomic(dgam, dgamma, sh);
+  block_reduce_cols_atomic(dbet, dbeta, sh);
+  block_reduce_cols_atomic(dty0, dtype, sh);
+  if (__syncthreads_or(any1 ? 1 : 0)) block_reduce_cols_atomic(dty1, dtype + H, sh);
+}
+
+// ------------------------------------------------------------------------------------------------ column sums / cast
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int T, int N, int rows_per_block, float* __restrict__ out) {
+  const int c = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (c >= N) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, T);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    uint2 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const uint2*>(x + (int64_t)(r + k) * N + c));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f4_acc(acc, bf16x4_to_f4(v[k]));
+  }
+  for (; r < r1; ++r) f4_acc(acc, bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(x + (int64_t)r * N + c))));
+  red_add_v4(out + c, acc);
+}
+
+__global__ void cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src + i + 4));
+      *reinterpret_cast<uint4*>(dst + i) =
+          make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    } else {
+      for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+    }
+  }
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" int nbest_pack_batch(nbest_ctx* ctx, const int64_t* ids, const int64_t* seg_ids, int B, int S, int pos_mode,
+                                int32_t* lens, int32_t* cu_seqlens, int32_t* tokens, uint8_t* seg, int32_t* pos,
+                                int32_t* seq_of, uint8_t* key_valid, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, ids && lens && cu_seqlens && tokens && seg && pos && seq_of && key_valid, "null pointer");
+  NBEST_CHECK_ARG(ctx, B > 0 && S > 0, "empty batch");
+  NBEST_CHECK_ARG(ctx, pos_mode == 0 || pos_mode == 1, "pos_mode must be 0 (bert) or 1 (xlm-roberta)");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = (B + 7) / 8;
+  pack_lens_kernel<<<blocks, 256, 0, s>>>(ids, B, S, lens);
+  NBEST_CHECK_LAUNCH(ctx);
+  pack_scan_kernel<<<1, 1024, 0, s>>>(lens, B, cu_seqlens);
+  NBEST_CHECK_LAUNCH(ctx);
+  pack_scatter_kernel<<<blocks, 256, 0, s>>>(ids, seg_ids, B, S, pos_mode, cu_seqlens, tokens, seg, pos, seq_of, key_valid);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
+extern "C" int nbest_embed_ln_fwd(nbest_ctx* ctx, const int32_t* tokens, const uint8_t* seg, const int32_t* pos, int T,
+                                  const float* word, const float* posemb, const float* type, const float* gamma,
+                                  const float* beta, float eps, int hidden, void* y_bf16, float* mean, float* rstd,
+                                  float p_drop, uint32_t seed, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, hidden == H, "hidden must be 768");
+  NBEST_CHECK_ARG(ctx, tokens && seg && pos && word && posemb && type && gamma && beta && y_bf16 && mean && rstd, "null pointer");
+  NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
+  if (T <= 0) return NBEST_OK;
+  embed_ln_fwd_kernel<<<(T + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      tokens, seg, pos, T, word, posemb, type, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y_bf16), mean, rstd,
+      drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
+extern "C" int nbest_embed_ln_bwd(nbest_ctx* ctx, const int32_t* tokens, const uint8_t* seg, const int32_t* pos, int T,
+                                  const float* word, const float* posemb, const float* type, const float* gamma,
+                                  const float* mean, const float* rstd, int hidden, const void* dy_bf16, float p_drop,
+                                  uint32_t seed, float* dword, float* dpos, float* dtype, float* dgamma, float* dbeta,
+                                  int word_pad_row, int pos_pad_row, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, hidden == H, "hidden must be 768");
+  NBEST_CHECK_ARG(ctx, tokens && seg && pos && word && posemb && type && gamma && mean && rstd && dy_bf16, "null pointer");
+  NBEST_CHECK_ARG(ctx, dword && dpos && dtype && dgamma && dbeta, "null gradient pointer");
+  if (T <= 0) return NBEST_OK;
+  int blocks = (T + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  if (blocks > 2 * ctx->num_sms) blocks = 2 * ctx->num_sms;
+  embed_ln_bwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      tokens, seg, pos, T, word, posemb, type, gamma, mean, rstd, reinterpret_cast<const __nv_bfloat16*>(dy_bf16),
+      drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed, dword, dpos, dtype, dgamma, dbeta, word_pad_row, pos_pad_row);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
+extern "C" int nbest_ln_fwd(nbest_ctx* ctx, const void* x_bf16, const float* gamma, const float* beta, float eps, int T,
+                            int hidden, void* y_bf16, float* mean, float* rstd, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, hidden == H, "hidden must be 768");
+  NBEST_CHECK_ARG(ctx, x_bf16 && gamma && beta && y_bf16, "null pointer");
+  if (T <= 0) return NBEST_OK;
+  ln_fwd_kernel<<<(T + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x_bf16), gamma, beta, eps, T, reinterpret_cast<__nv_bfloat16*>(y_bf16), mean, rstd);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
+extern "C" int nbest_ln_bwd(nbest_ctx* ctx, const void* dy_bf16, const void* x_bf16, const float* mean, const float* rstd,
+                            const float* gamma, int T, int hidden, void* dx_bf16, void* dx_masked_bf16, float p_drop,
+                            uint32_t seed, float* dgamma, float* dbeta, float* dbias, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, hidden == H, "hidden must be 768");
+  NBEST_CHECK_ARG(ctx, dy_bf16 && x_bf16 && mean && rstd && gamma && dx_bf16 && dgamma && dbeta, "null pointer");
+  NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
+  NBEST_CHECK_ARG(ctx, !(p_drop > 0.f) || dx_masked_bf16, "p_drop > 0 needs dx_masked");
+  if (T <= 0) return NBEST_OK;
+  int blocks = (T + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  if (blocks > 2 * ctx->num_sms) blocks = 2 * ctx->num_sms;
+  ln_bwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16), mean, rstd, gamma, T,
+      reinterpret_cast<__nv_bfloat16*>(dx_bf16), p_drop > 0.f ? reinterpret_cast<__nv_bfloat16*>(dx_masked_bf16) : nullptr,
+      drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed, dgamma, dbeta, dbias);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
+extern "C" int nbest_colsum_bf16(nbest_ctx* ctx, const void* x_bf16, int T, int N, float* out, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, x_bf16 && out, "null pointer");
+  NBEST_CHECK_ARG(ctx, N > 0 && N % 4 == 0, "N must be a multiple of 4");
+  if (T <= 0) return NBEST_OK;
+  const int threads = 128;
+  const int gx = (N / 4 + threads - 1) / threads;
+  int gy = (4 * ctx->num_sms + gx - 1) / gx;
+  int rows_per_block = (T + gy - 1) / gy;
+  if (rows_per_block < 16) rows_per_block = 16;
+  gy = (T + rows_per_block - 1) / rows_per_block;
+  colsum_kernel<<<dim3(gx, gy), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x_bf16), T, N, rows_per_block, out);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
+extern "C" int nbest_cast_f32_bf16(nbest_ctx* ctx, const float* src, void* dst_bf16, int64_t n, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, src && dst_bf16, "null pointer");
+  NBEST_CHECK_ARG(ctx, (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst_bf16) & 15) == 0,
+                  "buffers must be 16-byte aligned");
+  if (n <= 0) return NBEST_OK;
+  int64_t blocks = (n / 8 + 255) / 256;
+  if (blocks > 8 * ctx->num_sms) blocks = 8 * ctx->num_sms;
+  if (blocks < 1) blocks = 1;
+  cast_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), n);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}

@@ -56,3 +56,178 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, epilogue=EPI_NONE, bias=No
         int(seed) & 0xFFFFFFFF, _stream())
     ctx.check(rc)
     return out
+
+
+def _seed(s):
+    return int(s) & 0xFFFFFFFF
+
+
+# ---------------------------------------------------------------------------------------------------------- packing
+class Packed:
+    """Packed variable-length batch (device tensors). T is a host int (one D2H read of cu_seqlens[-1] unless given)."""
+    __slots__ = ("B", "S", "T", "max_len", "lens", "cu_seqlens", "tokens", "seg", "pos", "seq_of", "key_valid")
+
+
+def pack_batch(ids, seg_ids=None, kind="bert", lens_host=None):
+    """ids [B,S] int64 CUDA, right padded -> Packed. See nbest_pack_batch."""
+    if ids.dtype != torch.int64 or ids.dim() != 2:
+        raise ValueError("ids must be an int64 [B,S] tensor")
+    ids = ids.contiguous()
+    if seg_ids is not None:
+        seg_ids = seg_ids.contiguous()
+    B, S = ids.shape
+    dev = ids.device
+    pk = Packed()
+    pk.B, pk.S = B, S
+    pk.lens = torch.empty(B, dtype=torch.int32, device=dev)
+    pk.cu_seqlens = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    cap = B * S
+    pk.tokens = torch.empty(cap, dtype=torch.int32, device=dev)
+    pk.seg = torch.empty(cap, dtype=torch.uint8, device=dev)
+    pk.pos = torch.empty(cap, dtype=torch.int32, device=dev)
+    pk.seq_of = torch.empty(cap, dtype=torch.int32, device=dev)
+    pk.key_valid = torch.empty(cap, dtype=torch.uint8, device=dev)
+    ctx = _ctx(ids)
+    ctx.check(_lib.lib().nbest_pack_batch(ctx.handle, _p(ids), _p(seg_ids), B, S, 1 if kind == "xlm-roberta" else 0,
+                                          _p(pk.lens), _p(pk.cu_seqlens), _p(pk.tokens), _p(pk.seg), _p(pk.pos),
+                                          _p(pk.seq_of), _p(pk.key_valid), _stream()))
+    if lens_host is not None and kind != "xlm-roberta":
+        pk.T = int(sum(lens_host))
+        pk.max_len = int(max(lens_host))
+    else:
+        lens_cpu = pk.lens.cpu()
+        pk.T = int(lens_cpu.sum())
+        pk.max_len = int(lens_cpu.max())
+    return pk
+
+
+# ---------------------------------------------------------------------------------------------------------- embed / LN
+def embed_ln_fwd(pk, word, posemb, type_emb, gamma, beta, eps, y, mean, rstd, p_drop=0.0, seed=0):
+    ctx = _ctx(word)
+    ctx.check(_lib.lib().nbest_embed_ln_fwd(ctx.handle, _p(pk.tokens), _p(pk.seg), _p(pk.pos), pk.T, _p(word), _p(posemb),
+                                            _p(type_emb), _p(gamma), _p(beta), float(eps), word.shape[1], _p(y), _p(mean),
+                                            _p(rstd), float(p_drop), _seed(seed), _stream()))
+
+
+def embed_ln_bwd(pk, word, posemb, type_emb, gamma, mean, rstd, dy, dword, dpos, dtype, dgamma, dbeta, p_drop=0.0, seed=0,
+                 word_pad_row=-1, pos_pad_row=-1, T=None):
+    ctx = _ctx(word)
+    ctx.check(_lib.lib().nbest_embed_ln_bwd(ctx.handle, _p(pk.tokens), _p(pk.seg), _p(pk.pos), pk.T if T is None else T,
+                                            _p(word), _p(posemb), _p(type_emb), _p(gamma), _p(mean), _p(rstd), word.shape[1],
+                                            _p(dy), float(p_drop), _seed(seed), _p(dword), _p(dpos), _p(dtype), _p(dgamma),
+                                            _p(dbeta), int(word_pad_row), int(pos_pad_row), _stream()))
+
+
+def ln_fwd(x, gamma, beta, eps, y, mean=None, rstd=None, T=None):
+    ctx = _ctx(x)
+    ctx.check(_lib.lib().nbest_ln_fwd(ctx.handle, _p(x), _p(gamma), _p(beta), float(eps), x.shape[0] if T is None else T,
+                                      x.shape[1], _p(y), _p(mean), _p(rstd), _stream()))
+
+
+def ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dx_masked=None, dbias=None, p_drop=0.0, seed=0, T=None):
+    ctx = _ctx(x)
+    ctx.check(_lib.lib().nbest_ln_bwd(ctx.handle, _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma),
+                                      x.shape[0] if T is None else T, x.shape[1], _p(dx), _p(dx_masked), float(p_drop),
+                                      _seed(seed), _p(dgamma), _p(dbeta), _p(dbias), _stream()))
+
+
+def colsum(x, out, T=None):
+    ctx = _ctx(x)
+    ctx.check(_lib.lib().nbest_colsum_bf16(ctx.handle, _p(x), x.shape[0] if T is None else T, x.shape[1], _p(out), _stream()))
+
+
+def cast_f32_bf16(src, dst):
+    ctx = _ctx(src)
+    ctx.check(_lib.lib().nbest_cast_f32_bf16(ctx.handle, _p(src), _p(dst), src.numel(), _stream()))
+
+
+# ---------------------------------------------------------------------------------------------------------- attention
+def attn_fwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out, lse, p_drop=0.0, seed=0):
+    ctx = _ctx(qkv)
+    ctx.check(_lib.lib().nbest_attn_varlen_fwd(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
+                                               _p(out), _p(lse), float(p_drop), _seed(seed), _stream()))
+
+
+def attn_bwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out, dout, lse, dqkv, delta_ws, p_drop=0.0, seed=0):
+    ctx = _ctx(qkv)
+    ctx.check(_lib.lib().nbest_attn_varlen_bwd(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
+                                               _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta_ws), float(p_drop), _seed(seed),
+                                               _stream()))
+
+
+# ---------------------------------------------------------------------------------------------------------- STC head / loss
+class DeviceHierarchy:
+    """Label hierarchy tables on the device + the ctypes struct the C ABI takes (nbest_hierarchy)."""
+
+    def __init__(self, top2bottom, none_bottoms=(), device="cuda"):
+        t2b = {int(k): [int(x) for x in v] for k, v in top2bottom.items()}
+        self.top2bottom = t2b
+        self.n_top = len(t2b)
+        self.n_bottom = sum(len(v) for v in t2b.values())
+        self.group_tops = [k for k in sorted(t2b) if len(t2b[k]) >= 2]
+        self.n_groups = len(self.group_tops)
+        grp_off = [self.n_top]
+        for k in self.group_tops:
+            grp_off.append(grp_off[-1] + len(t2b[k]))
+        self.n_cols = grp_off[-1]
+        col_group = [0] * self.n_top
+        col_bottom = [t2b[i][0] if len(t2b[i]) == 1 else -1 for i in range(self.n_top)]
+        for g, k in enumerate(self.group_tops, start=1):
+            col_group += [g] * len(t2b[k])
+            col_bottom += t2b[k]
+        none_set = set(int(x) for x in none_bottoms)
+        none_col = [1 if (c >= self.n_top and col_bottom[c] in none_set) else 0 for c in range(self.n_cols)]
+        self.grp_off_host, self.col_bottom_host = grp_off, col_bottom
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=device)
+        self.col_group = i32(col_group)
+        self.col_bottom = i32(col_bottom)
+        self.grp_off = i32(grp_off)
+        self.grp_top = i32(self.group_tops if self.group_tops else [0])
+        self.none_col = torch.tensor(none_col, dtype=torch.uint8, device=device)
+        self.struct = Hierarchy(self.n_top, self.n_bottom, self.n_groups, self.n_cols, self.col_group.data_ptr(),
+                                self.col_bottom.data_ptr(), self.grp_off.data_ptr(), self.grp_top.data_ptr())
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+def stc_head_fwd(x, cu_seqlens, B, W, bias, hier, cls, logits, top, bottom, final, decode=None, p_drop=0.0, seed=0):
+    ctx = _ctx(x)
+    ctx.check(_lib.lib().nbest_stc_head_fwd(ctx.handle, _p(x), _p(cu_seqlens), B, x.shape[1], _p(W), _p(bias), hier.ref(),
+                                            _p(hier.none_col), float(p_drop), _seed(seed), _p(cls), _p(logits), _p(top),
+                                            _p(bottom), _p(final), _p(decode), _stream()))
+
+
+def stc_loss_fwd_bwd(logits, labels, hier, losses, dlogits, asr_cls=None, trans_cls=None, mse_scale=1.0, d_asr=None,
+                     d_trans=None):
+    ctx = _ctx(logits)
+    ctx.check(_lib.lib().nbest_stc_loss_fwd_bwd(ctx.handle, _p(logits), _p(labels), logits.shape[0], hier.ref(), _p(asr_cls),
+                                                _p(trans_cls), asr_cls.shape[1] if asr_cls is not None else 768,
+                                                float(mse_scale), _p(losses), _p(dlogits), _p(d_asr), _p(d_trans), _stream()))
+
+
+def stc_scores_bwd(top, bottom, d_top, d_bottom, d_final, hier, dlogits):
+    ctx = _ctx(top)
+    ctx.check(_lib.lib().nbest_stc_scores_bwd(ctx.handle, _p(top), _p(bottom), _p(d_top), _p(d_bottom), _p(d_final),
+                                              top.shape[0], hier.ref(), _p(dlogits), _stream()))
+
+
+def stc_head_bwd(dlogits, cls, W, hier, dW, dbias, dcls, accumulate_dcls=False, p_drop=0.0, seed=0):
+    ctx = _ctx(cls)
+    ctx.check(_lib.lib().nbest_stc_head_bwd(ctx.handle, _p(dlogits), _p(cls), _p(W), cls.shape[0], cls.shape[1], hier.ref(),
+                                            float(p_drop), _seed(seed), _p(dW), _p(dbias), _p(dcls), int(accumulate_dcls),
+                                            _stream()))
+
+
+def cls_scatter(dcls, cu_seqlens, B, T, dx):
+    ctx = _ctx(dcls)
+    ctx.check(_lib.lib().nbest_cls_scatter(ctx.handle, _p(dcls), _p(cu_seqlens), B, T, dcls.shape[1], _p(dx), _stream()))
+
+
+# ---------------------------------------------------------------------------------------------------------- BertAdam
+def bertadam_step(p, g, m, v, p_bf16, tensors_dev, n_tensors, chunks_dev, n_chunks, norms_ws, sched, b1=0.9, b2=0.999,
+                  eps=1e-6, max_grad_norm=1.0):
+    ctx = _ctx(p)
+    ctx.check(_lib.lib().nbest_bertadam_step(ctx.handle, _p(p), _p(g), _p(m), _p(v), _p(p_bf16), _p(tensors_dev), n_tensors,
+                                             _p(chunks_dev), n_chunks, _p(norms_ws), float(sched), float(b1), float(b2),
+                                             float(eps), float(max_grad_norm), _stream()))

@@ -231,9 +231,11 @@ def encoder_forward(params, cfg, input_ids, token_type_ids=None, drop=None, pref
     else:
         pos_ids = torch.arange(S).unsqueeze(0).expand(B, S)
         tt = token_type_ids if token_type_ids is not None else torch.zeros_like(input_ids)
-    x = (F.embedding(input_ids, P("embeddings.word_embeddings.weight"))
+    # nn.Embedding(padding_idx=...) rows never receive gradient: word[pad] always, position[1] on XLM-R
+    x = (F.embedding(input_ids, P("embeddings.word_embeddings.weight"), padding_idx=cfg.pad_token_id)
          + F.embedding(tt, P("embeddings.token_type_embeddings.weight"))
-         + F.embedding(pos_ids, P("embeddings.position_embeddings.weight")))
+         + F.embedding(pos_ids, P("embeddings.position_embeddings.weight"),
+                       padding_idx=1 if cfg.kind == "xlm-roberta" else None))
     x = _ln(x, P("embeddings.LayerNorm.weight"), P("embeddings.LayerNorm.bias"), cfg.ln_eps)
     if drop is not None:
         x = drop(x, "emb")
@@ -302,8 +304,10 @@ def model_forward(params, cfg, hier, input_ids, trans_input_ids=None, seg_ids=No
 # A6: losses (n_best_asr_bert.py:145-195, utils/STC_util.py:4-51)
 # ----------------------------------------------------------------------------------------------------------------
 def _bce_sum(p, t):
-    """torch.nn.BCELoss(reduction='sum'): each log clamped at -100."""
-    return -(t * torch.clamp(torch.log(p), min=-100.0) + (1 - t) * torch.clamp(torch.log(1 - p), min=-100.0)).sum()
+    """torch.nn.BCELoss(reduction='sum') (n_best_asr_bert.py:572): forward -(t*max(log p,-100) + (1-t)*max(log(1-p),-100)),
+    backward the ATen closed form (p-t)/max(p(1-p),1e-12). The torch op itself is used so that saturated scores
+    differentiate exactly as they do for the reference (a hand-written log+clamp gives 0/0 there)."""
+    return F.binary_cross_entropy(p, t, reduction="sum")
 
 
 def total_loss(hier, top, bottoms, final, labels, asr_cls=None, trans_cls=None, add_l2_loss=False):

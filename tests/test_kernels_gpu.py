@@ -1,0 +1,479 @@
+"""Per-kernel parity of the CUDA path (through the C ABI) against fp32 torch / the oracle on the same seeded inputs."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+H = 768
+
+
+def _hier_json():
+    return json.load(open(os.path.join(GOLD, "dstc2_hierarchy.json")))
+
+
+def _rel(a, b):
+    return (a.double() - b.double()).abs().max().item() / max(b.double().abs().max().item(), 1e-30)
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def _rand_ids(B, S, lens, pad, lo, hi, seed, first=None):
+    g = np.random.RandomState(seed)
+    ids = np.full((B, S), pad, dtype=np.int64)
+    seg = np.zeros((B, S), dtype=np.int64)
+    for b, L in enumerate(lens):
+        ids[b, :L] = g.randint(lo, hi, size=L)
+        if first is not None and L > 0:
+            ids[b, 0] = first
+        seg[b, L // 3:L] = 1
+    return ids, seg
+
+
+# ------------------------------------------------------------------------------------------------------------ packing
+@pytest.mark.parametrize("kind", ["bert", "xlm-roberta"])
+def test_pack_batch_bit_exact(kind):
+    from nbest_b200 import ops
+    from oracle import stc_oracle as O
+    lens = [1, 7, 33, 64, 65, 128, 2, 90, 31, 32]
+    pad, first = (1, 0) if kind == "xlm-roberta" else (0, 101)
+    ids, seg = _rand_ids(len(lens), 128, lens, pad, 5, 30000, 0, first)
+    if kind == "xlm-roberta":
+        ids[3, 10] = 1      # an in-sequence <pad> id shifts the XLM-R position ids after it
+    ref = O.pack_batch(ids, seg, kind)
+    pk = ops.pack_batch(torch.from_numpy(ids).cuda(), torch.from_numpy(seg).cuda(), kind)
+    T = ref["T"]
+    assert pk.T == T
+    assert np.array_equal(pk.lens.cpu().numpy(), ref["lens"])
+    assert np.array_equal(pk.cu_seqlens.cpu().numpy(), ref["cu_seqlens"])
+    for name in ("tokens", "seg", "pos", "seq_of", "key_valid"):
+        assert np.array_equal(getattr(pk, name)[:T].cpu().numpy(), ref[name]), name
+
+
+def test_pack_matches_reference_prepare_inputs_fixture():
+    """Un-padding the reference's own padded tensors (golden fixture made by utils/bert_xlnet_inputs.py)."""
+    from nbest_b200 import ops
+    fx = np.load(os.path.join(GOLD, "packing_valid24.npz"))
+    ids, seg, lens = fx["ids_default"], fx["seg_default"], fx["lens_default"]
+    pk = ops.pack_batch(torch.from_numpy(ids).cuda(), torch.from_numpy(seg).cuda(), "bert")
+    assert np.array_equal(pk.lens.cpu().numpy(), lens.astype(np.int32))
+    tok = pk.tokens[:pk.T].cpu().numpy()
+    sg = pk.seg[:pk.T].cpu().numpy()
+    cu = pk.cu_seqlens.cpu().numpy()
+    for b in range(ids.shape[0]):
+        assert np.array_equal(tok[cu[b]:cu[b + 1]], ids[b, :lens[b]])
+        assert np.array_equal(sg[cu[b]:cu[b + 1]], seg[b, :lens[b]])
+    ids2 = fx["ids_nosys"]
+    pk2 = ops.pack_batch(torch.from_numpy(ids2).cuda(), None, "bert")
+    assert np.array_equal(pk2.lens.cpu().numpy(), fx["lens_nosys"].astype(np.int32))
+    assert int(pk2.seg[:pk2.T].sum()) == 0
+
+
+# ------------------------------------------------------------------------------------------------------------ embed + LN
+def _embed_setup(kind, seed=0):
+    from nbest_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    V, P, TV = 2000, 140, (1 if kind == "xlm-roberta" else 2)
+    word = torch.randn(V, H, device="cuda", generator=g) * 0.5
+    posemb = torch.randn(P, H, device="cuda", generator=g) * 0.5
+    typ = torch.randn(TV, H, device="cuda", generator=g) * 0.5
+    gamma = 1 + 0.1 * torch.randn(H, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(H, device="cuda", generator=g)
+    lens = [5, 64, 17, 128, 1, 77]
+    pad, first = (1, 0) if kind == "xlm-roberta" else (0, 101)
+    ids, seg = _rand_ids(len(lens), 128, lens, pad, 5, V, seed + 1, first)
+    if kind == "xlm-roberta":
+        seg[:] = 0
+    pk = ops.pack_batch(torch.from_numpy(ids).cuda(), torch.from_numpy(seg).cuda(), kind)
+    return pk, word, posemb, typ, gamma, beta
+
+
+@pytest.mark.parametrize("kind", ["bert", "xlm-roberta"])
+def test_embed_ln_fwd_bwd(kind):
+    from nbest_b200 import ops
+    pk, word, posemb, typ, gamma, beta = _embed_setup(kind)
+    T, eps = pk.T, 1e-12 if kind == "bert" else 1e-5
+    y = torch.empty(T, H, device="cuda", dtype=torch.bfloat16)
+    mean, rstd = torch.empty(T, device="cuda"), torch.empty(T, device="cuda")
+    ops.embed_ln_fwd(pk, word, posemb, typ, gamma, beta, eps, y, mean, rstd)
+    leaves = [t.clone().requires_grad_(True) for t in (word, posemb, typ, gamma, beta)]
+    tok, sg, ps = pk.tokens[:T].long(), pk.seg[:T].long(), pk.pos[:T].long()
+    x = leaves[0][tok] + leaves[2][sg] + leaves[1][ps]
+    ref = torch.nn.functional.layer_norm(x, (H,), leaves[3], leaves[4], eps)
+    assert _rel(y, ref) < 6e-3                                      # bf16 output rounding only
+    assert _rel(mean, x.mean(-1)) < 1e-5
+    dy = torch.randn(T, H, device="cuda").to(torch.bfloat16)
+    ref.backward(dy.float())
+    dword, dpos, dtyp = torch.zeros_like(word), torch.zeros_like(posemb), torch.zeros_like(typ)
+    dgamma, dbeta = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
+    wpad, ppad = (1, 1) if kind == "xlm-roberta" else (0, -1)
+    ops.embed_ln_bwd(pk, word, posemb, typ, gamma, mean, rstd, dy, dword, dpos, dtyp, dgamma, dbeta, word_pad_row=wpad,
+                     pos_pad_row=ppad)
+    gw, gp = leaves[0].grad.clone(), leaves[1].grad.clone()
+    gw[wpad] = 0                                                     # nn.Embedding(padding_idx) rows get no gradient
+    if ppad >= 0:
+        gp[ppad] = 0
+    assert _rel(dword, gw) < 1e-4 and _rel(dpos, gp) < 1e-4
+    assert _rel(dtyp, leaves[2].grad) < 1e-4
+    assert _rel(dgamma, leaves[3].grad) < 1e-4 and _rel(dbeta, leaves[4].grad) < 1e-4
+
+
+def test_embed_dropout_rate_and_backward_mask():
+    from nbest_b200 import ops
+    pk, word, posemb, typ, gamma, beta = _embed_setup("bert", 3)
+    T = pk.T
+    y0 = torch.empty(T, H, device="cuda", dtype=torch.bfloat16)
+    y1 = torch.empty_like(y0)
+    mean, rstd = torch.empty(T, device="cuda"), torch.empty(T, device="cuda")
+    ops.embed_ln_fwd(pk, word, posemb, typ, gamma, beta, 1e-12, y0, mean, rstd)
+    ops.embed_ln_fwd(pk, word, posemb, typ, gamma, beta, 1e-12, y1, mean, rstd, p_drop=0.1, seed=77)
+    big = y0.float().abs() > 0.05
+    dropped = (y1 == 0) & big
+    assert abs(dropped.sum().item() / big.sum().item() - 0.1) < 0.01
+    kept = (~dropped) & big
+    assert _rel(y1.float()[kept], y0.float()[kept] / 0.9) < 1e-2
+    # backward uses the same mask: gradient of beta-free sum over dropped positions must vanish
+    dy = torch.ones(T, H, device="cuda", dtype=torch.bfloat16)
+    z = lambda t: torch.zeros_like(t)
+    dgamma, dbeta = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
+    ops.embed_ln_bwd(pk, word, posemb, typ, gamma, mean, rstd, dy, z(word), z(posemb), z(typ), dgamma, dbeta, p_drop=0.1, seed=77)
+    keep_cnt = (y1 != 0).float().sum(0) + ((y1 == 0) & ~big & (y0 == 0)).float().sum(0)
+    assert (dbeta / (1 / 0.9) - keep_cnt).abs().max().item() <= 3.0          # dbeta[j] = #kept(j)/(1-p) up to tiny values
+
+
+def test_ln_fwd_bwd_with_masked_output():
+    from nbest_b200 import ops
+    T = 1003
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = (torch.randn(T, H, device="cuda", generator=g) * 2 + 0.3).to(torch.bfloat16)
+    gamma = (1 + 0.1 * torch.randn(H, device="cuda", generator=g)).requires_grad_(True)
+    beta = (0.1 * torch.randn(H, device="cuda", generator=g)).requires_grad_(True)
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(T, device="cuda"), torch.empty(T, device="cuda")
+    ops.ln_fwd(x, gamma, beta, 1e-12, y, mean, rstd)
+    xf = x.float().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xf, (H,), gamma, beta, 1e-12)
+    assert _rel(y, ref) < 6e-3
+    dy = torch.randn(T, H, device="cuda", generator=g).to(torch.bfloat16)
+    ref.backward(dy.float())
+    dx = torch.empty_like(x)
+    dgamma, dbeta, dbias = (torch.zeros(H, device="cuda") for _ in range(3))
+    ops.ln_bwd(dy, x, mean, rstd, gamma.detach(), dx, dgamma, dbeta, dbias=dbias)
+    assert _rel(dx, xf.grad) < 6e-3
+    assert _rel(dgamma, gamma.grad) < 1e-4 and _rel(dbeta, beta.grad) < 1e-4
+    assert _rel(dbias, xf.grad.sum(0)) < 1e-3
+    # masked variant: dx_masked = dx * keep/(1-p) with the SAME mask the GEMM epilogue applies for (p, seed)
+    dxm = torch.empty_like(x)
+    dbias2 = torch.zeros(H, device="cuda")
+    ops.ln_bwd(dy, x, mean, rstd, gamma.detach(), dx, torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda"),
+               dx_masked=dxm, dbias=dbias2, p_drop=0.2, seed=4242)
+    a = torch.ones(T, 64, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(H, 64, device="cuda", dtype=torch.bfloat16)
+    ones = ops.gemm(a, w, epilogue=ops.EPI_BIAS_DROP_RES, bias=torch.ones(H, device="cuda"),
+                    aux=torch.zeros(T, H, device="cuda", dtype=torch.bfloat16), p_drop=0.2, seed=4242)   # = mask/(1-p)
+    assert _rel(dxm.float(), dx.float() * ones.float()) < 1e-2
+    assert _rel(dbias2, (xf.grad * ones.float()).sum(0)) < 5e-3
+
+
+def test_colsum_and_cast():
+    from nbest_b200 import ops
+    x = torch.randn(2777, 2304, device="cuda").to(torch.bfloat16)
+    out = torch.ones(2304, device="cuda")
+    ops.colsum(x, out)
+    assert _rel(out, 1 + x.float().sum(0)) < 1e-4
+    src = torch.randn(1_000_003 + 5, device="cuda")[:1_000_003 + 5]
+    dst = torch.empty(src.numel(), device="cuda", dtype=torch.bfloat16)
+    ops.cast_f32_bf16(src, dst)
+    assert torch.equal(dst, src.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------------------ attention
+def _attn_ref(qkv, cu, key_valid, heads, dout=None):
+    T = qkv.shape[0]
+    q, k, v = [t.view(T, heads, 64).float() for t in qkv.float().split(heads * 64, dim=1)]
+    q, k, v = (t.detach().requires_grad_(True) for t in (q, k, v))
+    outs = []
+    for b in range(len(cu) - 1):
+        s, e = int(cu[b]), int(cu[b + 1])
+        sc = torch.einsum("qhd,khd->hqk", q[s:e], k[s:e]) / 8.0
+        sc = sc.masked_fill(~key_valid[s:e].bool()[None, None, :], float("-inf"))
+        outs.append(torch.einsum("hqk,khd->qhd", torch.softmax(sc, -1), v[s:e]))
+    out = torch.cat(outs, 0).reshape(T, heads * 64)
+    grads = None
+    if dout is not None:
+        out.backward(dout.float())
+        grads = torch.cat([q.grad.reshape(T, -1), k.grad.reshape(T, -1), v.grad.reshape(T, -1)], 1)
+    return out.detach(), grads
+
+
+@pytest.mark.parametrize("lens", [[1, 17, 64, 65, 128], [200, 3, 512, 129], [46] * 9])
+def test_attention_fwd_bwd(lens):
+    from nbest_b200 import ops
+    heads, B = 12, len(lens)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    T = int(cu[-1])
+    g = torch.Generator(device="cuda").manual_seed(sum(lens))
+    qkv = (torch.randn(T, 3 * heads * 64, device="cuda", generator=g) * 1.2).to(torch.bfloat16)
+    key_valid = torch.ones(T, dtype=torch.uint8, device="cuda")
+    for b in range(B):
+        if lens[b] > 4:
+            key_valid[int(cu[b])] = 0 if b % 2 else 1          # XLM-R style: first token masked as a key
+            key_valid[int(cu[b]) + 3] = 0
+    cu_d = torch.from_numpy(cu).cuda()
+    out = torch.empty(T, heads * 64, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(heads, T, device="cuda")
+    ops.attn_fwd(qkv, cu_d, key_valid, B, max(lens), heads, T, out, lse)
+    dout = torch.randn(T, heads * 64, device="cuda", generator=g).to(torch.bfloat16)
+    ref_out, ref_grads = _attn_ref(qkv, cu, key_valid, heads, dout)
+    assert _rel(out, ref_out) < 1e-2
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(heads, T, device="cuda")
+    ops.attn_bwd(qkv, cu_d, key_valid, B, max(lens), heads, T, out, dout, lse, dqkv, delta)
+    assert _rel(dqkv, ref_grads) < 2e-2
+    assert _cos(dqkv, ref_grads) > 0.9995
+    # key_valid = None means all keys valid
+    ops.attn_fwd(qkv, cu_d, None, B, max(lens), heads, T, out, lse)
+    ref2, _ = _attn_ref(qkv, cu, torch.ones_like(key_valid), heads)
+    assert _rel(out, ref2) < 1e-2
+
+
+def test_attention_dropout_forward_backward_consistent():
+    """With a fixed (seed-determined) mask O is linear in V, so <dO, O(V)> = <dV, V>; and the directional derivative
+    along dQ/dK matches a central difference. Both fail if forward and backward regenerate different masks."""
+    from nbest_b200 import ops
+    heads, lens = 12, [70, 128, 33]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    T, B = int(cu[-1]), len(lens)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    qkv = torch.randn(T, 3 * heads * 64, device="cuda", generator=g).to(torch.bfloat16)
+    cu_d = torch.from_numpy(cu).cuda()
+    p, seed = 0.3, 555
+
+    def fwd(t):
+        out = torch.empty(T, heads * 64, device="cuda", dtype=torch.bfloat16)
+        lse = torch.empty(heads, T, device="cuda")
+        ops.attn_fwd(t, cu_d, None, B, max(lens), heads, T, out, lse, p_drop=p, seed=seed)
+        return out, lse
+
+    out, lse = fwd(qkv)
+    out_nodrop = torch.empty_like(out)
+    ops.attn_fwd(qkv, cu_d, None, B, max(lens), heads, T, out_nodrop, torch.empty_like(lse))
+    assert _rel(out, out_nodrop) > 0.05                               # dropout really changed the result
+    dout = torch.randn(T, heads * 64, device="cuda", generator=g).to(torch.bfloat16)
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(qkv, cu_d, None, B, max(lens), heads, T, out, dout, lse, dqkv, torch.empty(heads, T, device="cuda"),
+                 p_drop=p, seed=seed)
+    v, dv = qkv[:, 2 * heads * 64:].double(), dqkv[:, 2 * heads * 64:].double()
+    lhs, rhs = (dout.double() * out.double()).sum().item(), (dv * v).sum().item()
+    assert abs(lhs - rhs) / abs(lhs) < 2e-2
+    # directional derivative in Q and K
+    direction = dqkv[:, :2 * heads * 64].float()                       # along the gradient: a large, coherent signal
+    direction = direction / direction.abs().mean()
+    eps = 0.05
+    plus, minus = qkv.float().clone(), qkv.float().clone()
+    plus[:, :2 * heads * 64] += eps * direction
+    minus[:, :2 * heads * 64] -= eps * direction
+    op, _ = fwd(plus.to(torch.bfloat16))
+    om, _ = fwd(minus.to(torch.bfloat16))
+    real_step = (plus.to(torch.bfloat16).double() - minus.to(torch.bfloat16).double())[:, :2 * heads * 64]
+    fd = ((op.double() - om.double()) * dout.double()).sum().item()
+    an = (dqkv[:, :2 * heads * 64].double() * real_step).sum().item()
+    assert abs(fd - an) / abs(an) < 0.08
+
+
+# ------------------------------------------------------------------------------------------------------------ head + loss
+def _head_setup(B=9, seed=0):
+    from nbest_b200 import ops
+    from oracle import stc_oracle as O
+    hj = _hier_json()
+    hier_o = O.Hierarchy({int(k): v for k, v in hj["top2bottom"].items()}, hj["none_bottoms"])
+    hier_d = ops.DeviceHierarchy(hj["top2bottom"], hj["none_bottoms"])
+    g = torch.Generator().manual_seed(seed)
+    params = {"clf.top_linear_layer.weight": torch.randn(hier_o.n_top, H, generator=g) * 0.08,
+              "clf.top_linear_layer.bias": torch.randn(hier_o.n_top, generator=g) * 0.5}
+    for k in hier_o.group_tops:
+        n = len(hier_o.top2bottom[k])
+        params["clf.linear_layers.lin_%d.weight" % k] = torch.randn(n, H, generator=g) * 0.08
+        params["clf.linear_layers.lin_%d.bias" % k] = torch.randn(n, generator=g) * 0.5
+    W = torch.cat([params["clf.top_linear_layer.weight"]] + [params["clf.linear_layers.lin_%d.weight" % k] for k in hier_o.group_tops])
+    bias = torch.cat([params["clf.top_linear_layer.bias"]] + [params["clf.linear_layers.lin_%d.bias" % k] for k in hier_o.group_tops])
+    lens = [3 + 5 * i for i in range(B)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    x = torch.randn(int(cu[-1]), H, generator=g).to(torch.bfloat16)
+    labels = torch.zeros(B, hier_o.n_bottom)
+    rs = np.random.RandomState(seed)
+    for b in range(B):
+        for t in rs.choice(np.arange(1, hier_o.n_top), size=rs.randint(0, 4), replace=False):
+            ids = hier_o.top2bottom[int(t)]
+            labels[b, ids[rs.randint(0, max(1, len(ids) - 1))]] = 1
+    return hier_o, hier_d, params, W, bias, cu, x, labels
+
+
+def _run_head(hier_d, x, cu, W, bias, B, p=0.0, seed=0):
+    from nbest_b200 import ops
+    dev = "cuda"
+    o = dict(cls=torch.empty(B, H, device=dev), logits=torch.empty(B, hier_d.n_cols, device=dev),
+             top=torch.empty(B, hier_d.n_top, device=dev), bottom=torch.empty(B, hier_d.n_cols - hier_d.n_top, device=dev),
+             final=torch.empty(B, hier_d.n_bottom, device=dev), decode=torch.empty(B, hier_d.n_bottom, dtype=torch.uint8, device=dev))
+    ops.stc_head_fwd(x.cuda(), torch.from_numpy(cu).cuda(), B, W.cuda(), bias.cuda(), hier_d, o["cls"], o["logits"], o["top"],
+                     o["bottom"], o["final"], o["decode"], p_drop=p, seed=seed)
+    return o
+
+
+def test_stc_head_forward_decode_and_loss_match_oracle():
+    from nbest_b200 import ops
+    from oracle import stc_oracle as O
+    hier_o, hier_d, params, W, bias, cu, x, labels = _head_setup()
+    B = len(cu) - 1
+    o = _run_head(hier_d, x, cu, W, bias, B)
+    f = x.float()[torch.from_numpy(cu[:-1]).long()]
+    assert torch.equal(o["cls"].cpu(), f)
+    fl = f.clone().requires_grad_(True)
+    pl = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    top, bottoms, final = O.head_forward(pl, hier_o, fl)
+    assert _rel(o["top"].cpu(), top) < 1e-5 and _rel(o["final"].cpu(), final) < 1e-5
+    assert _rel(o["bottom"].cpu(), torch.cat([bottoms["lin_%d" % k] for k in hier_o.group_tops], 1)) < 1e-5
+    assert np.array_equal(o["decode"].cpu().numpy(), O.decode(hier_o, top, bottoms))
+    # fused loss + gradient
+    trans = torch.randn(B, H)
+    total, terms = O.total_loss(hier_o, top, bottoms, final, labels, fl, trans, add_l2_loss=True)
+    total.backward()
+    losses = torch.zeros(4, device="cuda")
+    dlogits = torch.empty(B, hier_d.n_cols, device="cuda")
+    d_asr, d_trans = torch.empty(B, H, device="cuda"), torch.empty(B, H, device="cuda")
+    ops.stc_loss_fwd_bwd(o["logits"], labels.cuda(), hier_d, losses, dlogits, o["cls"], trans.cuda(), 1.0, d_asr, d_trans)
+    ref_terms = torch.tensor([float(terms["mse"]), float(terms["bce_final"]), float(terms["bce_top"]), float(terms["ce"])])
+    assert _rel(losses.cpu(), ref_terms) < 1e-5
+    dW = torch.zeros_like(W).cuda()
+    dbias = torch.zeros_like(bias).cuda()
+    dcls = d_asr.clone()
+    ops.stc_head_bwd(dlogits, o["cls"], W.cuda(), hier_d, dW, dbias, dcls, accumulate_dcls=True)
+    refW = torch.cat([pl["clf.top_linear_layer.weight"].grad] + [pl["clf.linear_layers.lin_%d.weight" % k].grad for k in hier_o.group_tops])
+    refb = torch.cat([pl["clf.top_linear_layer.bias"].grad] + [pl["clf.linear_layers.lin_%d.bias" % k].grad for k in hier_o.group_tops])
+    assert _rel(dW.cpu(), refW) < 1e-4 and _rel(dbias.cpu(), refb) < 1e-4
+    assert _rel(dcls.cpu(), fl.grad) < 1e-4
+    assert _rel(d_trans.cpu(), -2 * (f - trans) / (B * H)) < 1e-5
+    # cls scatter
+    T = int(cu[-1])
+    dx = torch.full((T, H), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.cls_scatter(dcls, torch.from_numpy(cu).cuda(), B, T, dx)
+    ref_dx = torch.zeros(T, H)
+    ref_dx[torch.from_numpy(cu[:-1]).long()] = dcls.cpu()
+    assert torch.equal(dx.cpu(), ref_dx.to(torch.bfloat16))
+
+
+def test_stc_loss_clamp_and_extreme_logits():
+    """BCELoss clamps each log at -100 (zero gradient in the clamped branch); saturated sigmoids must not give NaN."""
+    from nbest_b200 import ops
+    from oracle import stc_oracle as O
+    hier_o, hier_d, params, W, bias, cu, x, labels = _head_setup(B=4, seed=3)
+    B = 4
+    logits = torch.randn(B, hier_d.n_cols) * 3
+    logits[0, 2] = 200.0
+    logits[1, 3] = -200.0
+    logits[2, 40] = 150.0
+    zl = logits.clone().requires_grad_(True)
+    top = torch.sigmoid(zl[:, :hier_o.n_top])
+    bottoms = {"lin_%d" % k: torch.softmax(zl[:, hier_o.grp_off[g]:hier_o.grp_off[g + 1]], 1) for g, k in enumerate(hier_o.group_tops)}
+    cols = [None] * hier_o.n_bottom
+    for i in range(hier_o.n_top):
+        ids = hier_o.top2bottom[i]
+        for j, bb in enumerate(ids):
+            cols[bb] = top[:, i] * bottoms["lin_%d" % i][:, j] if len(ids) > 1 else top[:, i]
+    final = torch.stack(cols, 1)
+    total, terms = O.total_loss(hier_o, top, bottoms, final, labels)
+    total.backward()
+    losses = torch.zeros(4, device="cuda")
+    dlogits = torch.empty(B, hier_d.n_cols, device="cuda")
+    ops.stc_loss_fwd_bwd(logits.cuda(), labels.cuda(), hier_d, losses, dlogits)
+    assert torch.isfinite(dlogits).all()
+    assert _rel(losses.cpu()[1:], torch.tensor([float(terms["bce_final"]), float(terms["bce_top"]), float(terms["ce"])])) < 1e-5
+    assert _rel(dlogits.cpu(), zl.grad) < 1e-4
+    # generic scores backward (autograd drop-in path) reproduces the same gradient from upstream grads
+    top_d, bot_d = top.detach().clone().requires_grad_(True), {k: v.detach().clone().requires_grad_(True) for k, v in bottoms.items()}
+    cols = [None] * hier_o.n_bottom
+    for i in range(hier_o.n_top):
+        ids = hier_o.top2bottom[i]
+        for j, bb in enumerate(ids):
+            cols[bb] = top_d[:, i] * bot_d["lin_%d" % i][:, j] if len(ids) > 1 else top_d[:, i]
+    final_d = torch.stack(cols, 1).detach().requires_grad_(True)
+    t2, _ = O.total_loss(hier_o, top_d, bot_d, final_d, labels)
+    t2.backward()
+    dl2 = torch.empty_like(dlogits)
+    d_bottom = torch.cat([bot_d["lin_%d" % k].grad for k in hier_o.group_tops], 1)
+    ops.stc_scores_bwd(top.detach().cuda(), torch.cat([bottoms["lin_%d" % k] for k in hier_o.group_tops], 1).detach().cuda(),
+                       top_d.grad.cuda(), d_bottom.cuda(), final_d.grad.cuda(), hier_d, dl2)
+    assert _rel(dl2.cpu(), zl.grad) < 1e-4
+
+
+def test_stc_head_dropout_masks_are_independent_and_consistent():
+    from nbest_b200 import ops
+    hier_o, hier_d, params, W, bias, cu, x, labels = _head_setup(B=16, seed=5)
+    B = 16
+    o0 = _run_head(hier_d, x, cu, W, bias, B)
+    o1 = _run_head(hier_d, x, cu, W, bias, B, p=0.3, seed=11)
+    assert _rel(o1["logits"], o0["logits"]) > 0.05
+    # the backward regenerates the same masks: <dlogits, logits - bias> = <dW, W>  (logits are linear in W)
+    dl = torch.randn(B, hier_d.n_cols, device="cuda")
+    dW, dbias, dcls = torch.zeros_like(W).cuda(), torch.zeros_like(bias).cuda(), torch.empty(B, H, device="cuda")
+    ops.stc_head_bwd(dl, o1["cls"], W.cuda(), hier_d, dW, dbias, dcls, p_drop=0.3, seed=11)
+    lhs = (dl.double() * (o1["logits"].double() - bias.cuda().double())).sum().item()
+    rhs = (dW.double() * W.cuda().double()).sum().item()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-4
+    lhs2 = (dcls.double() * o1["cls"].double()).sum().item()                 # and linear in the feature
+    assert abs(lhs - lhs2) / abs(lhs) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------------------ BertAdam
+def test_bertadam_matches_oracle_trajectory():
+    from nbest_b200 import ops
+    from nbest_b200.optim import build_adam_tables
+    from oracle import stc_oracle as O
+    names = ["bert_encoder.a.weight", "bert_encoder.a.bias", "bert_encoder.pooler.dense.weight", "clf.top_linear_layer.weight",
+             "clf.x.LayerNorm.weight", "clf.odd.bias"]
+    shapes = [(300, 768), (768,), (64, 64), (30, 768), (768,), (75,)]
+    g = torch.Generator().manual_seed(1)
+    params = {n: torch.randn(s, generator=g) * 0.1 for n, s in zip(names, shapes)}
+    lr, bert_lr, warm, t_total = 1e-3, 3e-4, 0.1, 20
+    offsets, total = [], 0
+    for s in shapes:
+        offsets.append(total)
+        total += (int(np.prod(s)) + 63) // 64 * 64
+    flat_p = torch.zeros(total)
+    for n, o in zip(names, offsets):
+        flat_p[o:o + params[n].numel()] = params[n].flatten()
+    flat_p = flat_p.cuda()
+    flat_m, flat_v, flat_g = torch.zeros_like(flat_p), torch.zeros_like(flat_p), torch.zeros_like(flat_p)
+    flat_b = flat_p.to(torch.bfloat16)
+    spec = []
+    for n, s, o in zip(names, shapes, offsets):
+        lr_p, wd = O.param_hyper(n, lr, bert_lr)
+        spec.append(dict(offset=o, numel=int(np.prod(s)), lr=lr_p, weight_decay=wd, active="pooler" not in n))
+    tables = build_adam_tables(spec, "cuda", chunk=4096)
+    state, oparams = {}, {n: p.clone() for n, p in params.items()}
+    for step in range(6):
+        grads = {}
+        for i, n in enumerate(names):
+            scale = 10.0 if (step + i) % 2 == 0 else 1e-3                      # clipped and unclipped tensors
+            grads[n] = None if "pooler" in n else torch.randn(params[n].shape, generator=g) * scale
+        flat_g.zero_()
+        for n, o in zip(names, offsets):
+            if grads[n] is not None:
+                flat_g[o:o + grads[n].numel()] = grads[n].flatten().cuda()
+        O.bertadam_step(oparams, grads, state, lr, bert_lr, warm, t_total)
+        ops.bertadam_step(flat_p, flat_g, flat_m, flat_v, flat_b, tables["tensors"], tables["n_tensors"], tables["chunks"],
+                          tables["n_chunks"], tables["norms"], O.warmup_linear(step, t_total, warm))
+        for n, o in zip(names, offsets):
+            got = flat_p[o:o + oparams[n].numel()].cpu().view(oparams[n].shape)
+            assert (got - oparams[n]).abs().max().item() < 2e-6, (step, n)
+    assert torch.equal(flat_b, flat_p.to(torch.bfloat16))
+    pool = flat_p[offsets[2]:offsets[2] + 64 * 64].cpu().view(64, 64)
+    assert torch.equal(pool, params["bert_encoder.pooler.dense.weight"])      # grad None -> never touched
