@@ -124,9 +124,12 @@ int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a_mn_major, 
 int nbest_attn_varlen_fwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens, const uint8_t* key_valid,
                           int B, int max_len, int heads, int T, void* out_bf16, float* lse, float p_drop,
                           uint32_t seed, void* stream);
-/* Backward: dqkv [T, 3*heads*64] bf16 from dout; delta_ws [heads, T] fp32 scratch. */
+/* Backward: dqkv [T_active, 3*heads*64] bf16 from dout [T_active, heads*64]; delta_ws [heads, T] fp32 scratch.
+ * T is the forward's token count (stride of lse / delta_ws and part of the dropout index); the B sequences given
+ * here cover the first T_active <= T tokens (the gradient-carrying prefix: the ASR stream when the transcript
+ * stream is forward-only, n_best_asr_bert.py:166). */
 int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens, const uint8_t* key_valid,
-                          int B, int max_len, int heads, int T, const void* out_bf16, const void* dout_bf16,
+                          int B, int max_len, int heads, int T, int T_active, const void* out_bf16, const void* dout_bf16,
                           const float* lse, void* dqkv_bf16, float* delta_ws, float p_drop, uint32_t seed,
                           void* stream);
 
@@ -189,7 +192,7 @@ typedef struct {
   float weight_decay;
   int32_t active;   /* 0: grad is None in the reference (pooler) -> skipped entirely */
 } nbest_adam_tensor;
-/* chunks[] (device, int32 triples {tensor, start_lo, len}) tile the active tensors; start is relative to the tensor.
+/* chunks[] (device, int32 triples {tensor, start, len}) tile the active tensors; start is relative to the tensor.
  * norms_ws[n_tensors] fp32 scratch. sched = schedule.get_lr(step) computed by the host in double.
  * p_bf16 (nullable) receives the refreshed bf16 working copy of p. grad_scale multiplies g before use (1/R etc). */
 int nbest_bertadam_step(nbest_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16,

@@ -43,7 +43,7 @@ _SIGNATURES = {
     "nbest_gemm_bf16": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _i64, C.c_int, _vp, _i64, C.c_int, C.c_int, C.c_int,
                                   C.c_int, _vp, _vp, _i64, _vp, _f32, _u32, _vp]),
     "nbest_attn_varlen_fwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32, _u32, _vp]),
-    "nbest_attn_varlen_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp,
+    "nbest_attn_varlen_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp,
                                         _f32, _u32, _vp]),
     "nbest_stc_head_fwd": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.POINTER(Hierarchy), _vp, _f32, _u32,
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

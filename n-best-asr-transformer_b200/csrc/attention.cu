@@ -215,10 +215,10 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------ backward: delta
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, int T,
-                                  int heads, float* __restrict__ delta) {
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, int rows,
+                                  int T, int heads, float* __restrict__ delta) {
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (t >= T) return;
+  if (t >= rows) return;
   const int lane = threadIdx.x & 31;
   const int hd = heads * D;
   for (int c = lane * 8; c < hd; c += 256) {
@@ -418,8 +418,9 @@ extern "C" int nbest_attn_varlen_fwd(nbest_ctx* ctx, const void* qkv_bf16, const
 }
 
 extern "C" int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens,
-                                     const uint8_t* key_valid, int B, int max_len, int heads, int T, const void* out_bf16,
-                                     const void* dout_bf16, const float* lse, void* dqkv_bf16, float* delta_ws, float p_drop,
+                                     const uint8_t* key_valid, int B, int max_len, int heads, int T, int T_active,
+                                     const void* out_bf16, const void* dout_bf16, const float* lse, void* dqkv_bf16,
+                                     float* delta_ws, float p_drop,
                                      uint32_t seed, void* stream) {
   if (!ctx) return NBEST_EINVAL;
   NBEST_CHECK_ARG(ctx, qkv_bf16 && cu_seqlens && out_bf16 && dout_bf16 && lse && dqkv_bf16 && delta_ws, "null pointer");
@@ -431,8 +432,9 @@ extern "C" int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const
   const auto* o = reinterpret_cast<const __nv_bfloat16*>(out_bf16);
   const auto* g = reinterpret_cast<const __nv_bfloat16*>(dout_bf16);
   auto* dq = reinterpret_cast<__nv_bfloat16*>(dqkv_bf16);
-  if (T > 0) {
-    attn_delta_kernel<<<(T + 7) / 8, 256, 0, s>>>(o, g, T, heads, delta_ws);
+  NBEST_CHECK_ARG(ctx, T_active >= 0 && T_active <= T, "need 0 <= T_active <= T");
+  if (T_active > 0) {
+    attn_delta_kernel<<<(T_active + 7) / 8, 256, 0, s>>>(o, g, T_active, T, heads, delta_ws);
     NBEST_CHECK_LAUNCH(ctx);
   }
   const dim3 grid((max_len + BLK - 1) / BLK, heads, B);

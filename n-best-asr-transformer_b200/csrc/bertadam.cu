@@ -19,9 +19,10 @@ __global__ void __launch_bounds__(kThreads)
 adam_norm_kernel(const float* __restrict__ g, const nbest_adam_tensor* __restrict__ tensors, const int32_t* __restrict__ chunks,
                  float* __restrict__ norms) {
   const int ti = chunks[3 * blockIdx.x], start = chunks[3 * blockIdx.x + 1], len = chunks[3 * blockIdx.x + 2];
-  const float* gp = g + tensors[ti].offset + start;   // offset and start are multiples of 4 elements
+  const int64_t base = tensors[ti].offset + start;
+  const float* gp = g + base;
   float acc = 0.f;
-  const int n4 = len >> 2;
+  const int n4 = (base & 3) == 0 ? (len >> 2) : 0;   // float4 path only for 16-byte aligned chunks (tiny head biases are not)
   for (int i = threadIdx.x; i < n4; i += kThreads) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(gp) + i);
     acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
@@ -64,7 +65,7 @@ adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
   }
   const float lr_t = (float)(t.lr * sched);
   const float wd = t.weight_decay;
-  const int n4 = len >> 2;
+  const int n4 = (base & 3) == 0 ? (len >> 2) : 0;
   for (int i = threadIdx.x; i < n4; i += kThreads) {
     float4 pv = reinterpret_cast<float4*>(p + base)[i];
     const float4 gv = __ldg(reinterpret_cast<const float4*>(g + base) + i);

@@ -65,7 +65,8 @@ def _seed(s):
 # ---------------------------------------------------------------------------------------------------------- packing
 class Packed:
     """Packed variable-length batch (device tensors). T is a host int (one D2H read of cu_seqlens[-1] unless given)."""
-    __slots__ = ("B", "S", "T", "max_len", "lens", "cu_seqlens", "tokens", "seg", "pos", "seq_of", "key_valid")
+    __slots__ = ("B", "S", "T", "max_len", "lens", "cu_seqlens", "tokens", "seg", "pos", "seq_of", "key_valid",
+                 "B_asr", "T_asr", "max_len_asr")
 
 
 def pack_batch(ids, seg_ids=None, kind="bert", lens_host=None):
@@ -148,10 +149,11 @@ def attn_fwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out, lse, p_drop=
                                                _p(out), _p(lse), float(p_drop), _seed(seed), _stream()))
 
 
-def attn_bwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out, dout, lse, dqkv, delta_ws, p_drop=0.0, seed=0):
+def attn_bwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out, dout, lse, dqkv, delta_ws, p_drop=0.0, seed=0,
+             T_active=None):
     ctx = _ctx(qkv)
     ctx.check(_lib.lib().nbest_attn_varlen_bwd(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
-                                               _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta_ws), float(p_drop), _seed(seed),
+                                               T if T_active is None else T_active, _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta_ws), float(p_drop), _seed(seed),
                                                _stream()))
 
 

@@ -47,8 +47,6 @@ def build_adam_tables(spec, device, chunk=16384):
         arr[i].lr = float(s["lr"])
         arr[i].weight_decay = float(s["weight_decay"])
         arr[i].active = 1 if s["active"] else 0
-        if s["offset"] % 4 != 0:
-            raise ValueError("tensor offsets must be multiples of 4 elements")
         if s["active"]:
             for start in range(0, int(s["numel"]), chunk):
                 chunks.append((i, start, min(chunk, int(s["numel"]) - start)))
@@ -61,12 +59,16 @@ def build_adam_tables(spec, device, chunk=16384):
 class FlatBuffers:
     """One flat fp32 buffer each for parameters, gradients and the two Adam moments (+ optional bf16 working copy)."""
 
-    def __init__(self, shapes, device, with_bf16=True):
+    def __init__(self, shapes, device, with_bf16=True, aligns=None):
+        """aligns[i] (elements, default ALIGN) is the alignment of tensor i's first element; 1 packs it directly
+        behind its predecessor (used to keep the 11 STC-head biases one contiguous [171] vector)."""
         self.offsets, total = [], 0
-        for shp in shapes:
+        for k, shp in enumerate(shapes):
+            a = ALIGN if aligns is None else int(aligns[k])
+            total = (total + a - 1) // a * a
             self.offsets.append(total)
-            n = int(np.prod(shp)) if len(shp) else 1
-            total += (n + ALIGN - 1) // ALIGN * ALIGN
+            total += int(np.prod(shp)) if len(shp) else 1
+        total = (total + ALIGN - 1) // ALIGN * ALIGN
         self.total = total
         self.shapes = [tuple(s) for s in shapes]
         self.params = torch.zeros(total, dtype=torch.float32, device=device)
