@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Headline benchmark: train utterances/s (fwd + bwd + BertAdam step), BERT-base n-best STC, on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): BERT-base-uncased, 5-best hypotheses [SEP]-joined, max_len 128, batch 256 per GPU,
+synthetic DSTC2-shaped token ids (nbest_b200.synth), random-init weights, act-slot + value heads, both encoder streams as
+the reference runs them (transcript stream forward-only without --add_l2_loss), dropout on (0.1 / 0.1 / 0.3), BertAdam
+with the reference's per-tensor groups. One "step" = one optimizer step over one batch. Prints ONE JSON line (rank 0).
+
+  value      whole-job utterances/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        the same through the public trainer call with HOST (pinned) input buffers: H2D copies of the step's inputs
+             and a D2H read of the loss terms inside the timed region
+  roofline   dominant kernel = the tcgen05 GEMM (all instances of one step): algorithmic FLOPs / CUDA-event time of those
+             launches, against the measured sustained bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference path timed on this box's host cores on a bounded sample (rank 0, N=1)
+--impl reference times that CPU port alone (the reference is pure Python + PyTorch; its sources cannot travel to the box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "train utterances/s (fwd+bwd+step) BERT-base n-best STC"
+UNIT = "utterances/s"
+GEMM_FLOPS_PER_TOKEN_FWD = 169_869_312          # 2*(4*768^2 + 2*768*3072)*12   
+ATTN_FLOPS_PER_L2_FWD = 36_864                  # 4*768*12 per L^2
+
+
+def load_hierarchy():
+    with open(os.path.join(ROOT, "tests", "golden", "dstc2_hierarchy.json")) as f:
+        return json.load(f)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_sustained=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, tf_sustained=1400.0, tf_burst=1590.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ CPU port (oracle)
+def cpu_port_step_time(n_utt, steps, warmup, seed=999, threads=None):
+    """Times the oracle port of the reference training step (both streams, dropout on, fp32, BertAdam) on host cores."""
+    from oracle import stc_oracle as O
+    from nbest_b200.synth import synth_batch
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    hj = load_hierarchy()
+    hier = O.Hierarchy({int(k): v for k, v in hj["top2bottom"].items()}, hj["none_bottoms"])
+    cfg = O.EncoderConfig.bert_base()
+    params = O.init_params(cfg, hier, seed=seed, style="hf")
+    state = {}
+    hp = dict(lr=3e-5, bert_lr=3e-5, warmup=0.1, t_total=2300, add_l2_loss=False)
+
+    def drop(t, site):
+        return torch.nn.functional.dropout(t, 0.3 if site == "head" else 0.1, True)
+
+    times = []
+    for i in range(warmup + steps):
+        b = synth_batch("bert", cfg.vocab_size, hier, n_utt, 5, 128, seed + i)
+        t0 = time.perf_counter()
+        O.train_step(params, cfg, hier, b, state, hp, drop)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return float(np.median(times)), float(np.sum(times)), threads
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_utt = 16
+    med, total, threads = cpu_port_step_time(n_utt, args.steps, max(1, min(args.warmup, 2)))
+    v = n_utt / med
+    line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=med * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="bert-base n-best STC train step, 5 hyps, max_len 128, both streams, dropout on",
+                            batch_per_step=n_utt, device="cpu"),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind="port",
+                                  sample="%d-utterance batches of the same generator, %d timed steps" % (n_utt, args.steps)),
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().split("\n") if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                power.append(float(r[3]))
+                for n, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm),
+                    power_w_max=float(max(power)))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")
+    ap.add_argument("--hyps", type=int, default=5)
+    ap.add_argument("--max-len", type=int, default=128)
+    ap.add_argument("--dense", action="store_true", help="every sequence exactly max_len tokens (roofline worst case)")
+    ap.add_argument("--l2", action="store_true", help="--add_l2_loss: transcript stream with gradients + MSE term")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropout", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    from nbest_b200 import _lib, ops
+    from nbest_b200.model import EncoderSpec, TOD_ASR_Transformer_STC
+    from nbest_b200.optim import BertAdam
+    from nbest_b200.synth import synth_batch
+    from nbest_b200.trainer import DataParallelTrainer, init_distributed
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU port)")
+    rank, local, world = init_distributed()
+    dev = torch.device("cuda", local)
+    hj = load_hierarchy()
+    t2b = {int(k): v for k, v in hj["top2bottom"].items()}
+    drop = 0.0 if args.no_dropout else None
+    spec = EncoderSpec.bert_base() if drop is None else EncoderSpec.bert_base(hidden_dropout=0.0, attn_dropout=0.0)
+    model = TOD_ASR_Transformer_STC(spec=spec, top2bottom=t2b, dropout=0.3 if drop is None else 0.0, device=dev,
+                                    none_bottoms=hj["none_bottoms"], seed=999)
+    model.train()
+    groups = []
+    for n, p in model.named_parameters():                          # reference n_best_asr_bert.py:535-550
+        no_decay = any(nd in n for nd in ("bias", "LayerNorm.bias", "LayerNorm.weight"))
+        groups.append(dict(params=p, weight_decay=0.0 if no_decay else 0.01, lr=3e-5))
+    optim = BertAdam(groups, lr=3e-5, warmup=0.1, t_total=2300)
+    trainer = DataParallelTrainer(model, optim, add_l2_loss=args.l2)
+    ctx = _lib.context(local)
+
+    # ---- synthetic batches: pinned host copies (e2e) + device-resident copies (value)
+    NB = 4
+    host, devb, stats = [], [], []
+    keys = ("ids", "seg", "trans_ids", "trans_seg", "labels")
+    for i in range(NB):
+        b = synth_batch("bert", spec.vocab_size, model.hier, args.batch, args.hyps, args.max_len, seed=999 + 1000 * rank + i,
+                        dense=args.dense)
+        host.append({k: b[k].pin_memory() for k in keys} | dict(lens=b["lens"], trans_lens=b["trans_lens"]))
+        devb.append({k: b[k].to(dev) for k in keys} | dict(lens=b["lens"], trans_lens=b["trans_lens"]))
+        L = np.array(b["lens"], dtype=np.float64)
+        Lt = np.array(b["trans_lens"], dtype=np.float64)
+        stats.append((L.sum(), (L ** 2).sum(), Lt.sum(), (Lt ** 2).sum()))
+    h2d_bytes = int(np.mean([sum(h[k].numel() * h[k].element_size() for k in keys) for h in host]))
+
+    def step_dev(i):
+        b = devb[i % NB]
+        return trainer.step(b["ids"], b["labels"], b["trans_ids"], b["seg"], b["trans_seg"], b["lens"], b["trans_lens"])
+
+    def step_host(i):
+        h = host[i % NB]
+        d = {k: h[k].to(dev, non_blocking=True) for k in keys}
+        losses = trainer.step(d["ids"], d["labels"], d["trans_ids"], d["seg"], d["trans_seg"], h["lens"], h["trans_lens"])
+        return losses.cpu()                                         # D2H read of the step's loss terms (synchronises)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches()
+        e0.record()
+        for i in range(steps):
+            out = fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), ctx.launches() - l0, out
+
+    for i in range(args.warmup):
+        step_dev(i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches, last = timed(step_dev, args.steps)
+    clocks = sampler.stop() if sampler else None
+    for i in range(2):
+        step_host(i)
+    ms_e2e, _, last_losses = timed(step_host, args.steps)
+    if not bool(torch.isfinite(last_losses).all()):
+        raise SystemExit("non-finite loss in the benchmark step")
+
+    # ---- per-kernel roofline leg: two instrumented steps (CUDA events around every launch of ours)
+    ops.profile_start()
+    for i in range(2):
+        step_dev(i)
+    rec = ops.profile_stop()
+    agg = {}
+    for name, t, fl, by, meta in rec:
+        a = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
+        a[0] += t / 2
+        a[1] += fl / 2
+        a[2] += by / 2
+        a[3] += 1
+    n_params = sum(p.numel() for p in model.parameters() if p.grad is not None)
+    if "bertadam_step" in agg:
+        agg["bertadam_step"][2] = 32.0 * n_params
+
+    if rank == 0:
+        pk = peaks()
+        utt = world * args.batch * args.steps
+        value = utt / (ms / 1e3)
+        T, L2, Tt, Lt2 = np.mean([s[0] for s in stats]), np.mean([s[1] for s in stats]), np.mean([s[2] for s in stats]), \
+            np.mean([s[3] for s in stats])
+        alg = 3.0 * (GEMM_FLOPS_PER_TOKEN_FWD * T + ATTN_FLOPS_PER_L2_FWD * L2)                      # BASELINE.md formula (ASR stream)
+        alg_all = alg + (3.0 if args.l2 else 1.0) * (GEMM_FLOPS_PER_TOKEN_FWD * Tt + ATTN_FLOPS_PER_L2_FWD * Lt2)
+        step_s = ms / 1e3 / args.steps
+        gemm_ms = sum(agg[k][0] for k in agg if k.startswith("gemm"))
+        gemm_fl = sum(agg[k][1] for k in agg if k.startswith("gemm"))
+        achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        kernels = {k: dict(ms_per_step=round(v[0], 4), launches_per_step=v[3] // 2,
+                           tflops=round(v[1] / (v[0] * 1e-3) / 1e12, 1) if v[1] else None,
+                           gbs=round(v[2] / (v[0] * 1e-3) / 1e9, 1) if v[2] else None) for k, v in sorted(agg.items())}
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+            config=dict(workload="BERT-base-uncased n-best STC bf16 packed varlen, batch %d/GPU, %d hyps, max_len %d%s%s" % (
+                args.batch, args.hyps, args.max_len, ", dense" if args.dense else "", ", add_l2_loss" if args.l2 else ""),
+                global_batch=world * args.batch, tokens_per_step_asr=float(T), tokens_per_step_transcript=float(Tt),
+                parallelism="dp%d" % world, dropout="off" if args.no_dropout else "0.1/0.1/0.3",
+                streams="asr fwd+bwd, transcript %s" % ("fwd+bwd" if args.l2 else "fwd only (as the reference)"),
+                l2_flush="per-step working set (activations + 438 MB fp32 weights + Adam state, > 4 GB) exceeds the 126 MB L2"),
+            clocks=clocks,
+            e2e=dict(value=utt / (ms_e2e / 1e3), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=16,
+                     ms_per_step=ms_e2e / args.steps),
+            gpu_launches=int(launches),
+            roofline=dict(bound="tensor", kernel="gemm_kernel (tcgen05, all instances of one step)", achieved=achieved,
+                          peak=pk["tf_sustained"], unit="TFLOP/s", frac=achieved / pk["tf_sustained"], traffic=None,
+                          peak_source=pk["src"] + " bf16_tflops_sustained", gemm_ms_per_step=gemm_ms,
+                          gemm_share_of_step=gemm_ms / (step_s * 1e3)),
+            tc_util=dict(asr_stream_formula=alg / (step_s * pk["tf_sustained"] * 1e12),
+                         all_executed_streams=alg_all / (step_s * pk["tf_sustained"] * 1e12)),
+            kernels=kernels)
+        if world == 1 and not args.no_cpu_baseline:
+            n_utt = 32
+            med, total, threads = cpu_port_step_time(n_utt, 2, 1)
+            line["cpu_baseline"] = dict(value=n_utt / med, unit=UNIT, cores=threads, kind="port",
+                                        sample="%d-utterance batch (BASELINE configs[0] shape), 1 warm-up + 2 timed steps, %.1f s" % (
+                                            n_utt, total), ms_per_step=med * 1e3)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -404,10 +404,18 @@ class TOD_ASR_Transformer_STC(nn.Module):
             ops.gemm(dqkv, w["h_wqkv"], b_mn_major=True, epilogue=ops.EPI_ADD, aux=dpre, out=dx)   # dx was consumed above
             ops.gemm(dqkv, A(L.x_in), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_wqkv"])
             ops.colsum(dqkv, w["g_bqkv"], T=T_act)
+            self._notify("layer%d" % l)
         em = self._emb
         ops.embed_ln_bwd(pk, em["p_word"], em["p_pos"], em["p_type"], em["p_gamma"], sv.mean0, sv.rstd0, dx, em["g_word"],
                          em["g_pos"], em["g_type"], em["g_gamma"], em["g_beta"], p_h, self._seed(0, 15),
                          word_pad_row=s.pad_token_id, pos_pad_row=1 if s.kind == "xlm-roberta" else -1, T=T_act)
+        self._notify("emb")
+
+    def _notify(self, bucket):
+        """Tell the data-parallel trainer that every gradient kernel of `bucket` has been enqueued."""
+        hook = getattr(self, "_grad_ready_hook", None)
+        if hook is not None:
+            hook(bucket)
 
     # ------------------------------------------------------------------------------------------------ head
     def _head_forward(self, sv, B, row0=0):
@@ -434,6 +442,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
         dcls_head = torch.empty((B, H), device=dev, dtype=torch.float32)
         ops.stc_head_bwd(dlogits, ho.cls, self._head["p_w"], self.hier, self._head["g_w"], self._head["g_b"], dcls_head,
                          accumulate_dcls=False, p_drop=ho.p, seed=ho.seed)
+        self._notify("head")
         d_asr, d_trans = (None, dcls_head) if head_on_trans else (dcls_head, None)
         if d_cls_asr is not None:
             d_asr = d_cls_asr if d_asr is None else d_asr + d_cls_asr

@@ -12,6 +12,43 @@ from ._lib import (EPI_ACCUM_F32, EPI_ADD, EPI_BIAS, EPI_BIAS_DROP_RES, EPI_BIAS
                    AdamTensor, Hierarchy)
 
 
+# Optional per-call timing (bench.py's roofline leg): ops.profile_start() makes every wrapper bracket its launch with
+# CUDA events on the launching stream; ops.profile_stop() returns [(name, ms, flops, bytes, meta)].
+_PROF = None
+
+
+def profile_start():
+    global _PROF
+    _PROF = []
+
+
+def profile_stop():
+    global _PROF
+    rec, _PROF = _PROF, None
+    torch.cuda.synchronize()
+    return [(n, e0.elapsed_time(e1), fl, by, meta) for n, e0, e1, fl, by, meta in rec]
+
+
+class _Timed:
+    __slots__ = ("name", "flops", "bytes", "meta", "e0")
+
+    def __init__(self, name, flops=0.0, nbytes=0.0, meta=None):
+        self.name, self.flops, self.bytes, self.meta = name, flops, nbytes, meta
+
+    def __enter__(self):
+        if _PROF is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROF is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _PROF.append((self.name, self.e0, e1, self.flops, self.bytes, self.meta))
+        return False
+
+
 def _ctx(t):
     if not t.is_cuda:
         raise RuntimeError("nbest_b200 ops need CUDA tensors (no CPU fallback)")
@@ -50,10 +87,12 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, epilogue=EPI_NONE, bias=No
         out = torch.empty((M, N), device=a.device,
                           dtype=torch.float32 if epilogue == EPI_ACCUM_F32 else torch.bfloat16)
     ctx = _ctx(a)
-    rc = _lib.lib().nbest_gemm_bf16(
-        ctx.handle, _p(a), a.stride(0), int(a_mn_major), _p(b), b.stride(0), int(b_mn_major), _p(out), out.stride(0),
-        M, N, K, int(epilogue), _p(bias), _p(aux), aux.stride(0) if aux is not None else 0, _p(out2), float(p_drop),
-        int(seed) & 0xFFFFFFFF, _stream())
+    kind = "gemm_wgrad" if a_mn_major else ("gemm_dgrad" if b_mn_major else "gemm_fwd")
+    with _Timed(kind, 2.0 * M * N * K, 0.0, (M, N, K, int(epilogue))):
+        rc = _lib.lib().nbest_gemm_bf16(
+            ctx.handle, _p(a), a.stride(0), int(a_mn_major), _p(b), b.stride(0), int(b_mn_major), _p(out), out.stride(0),
+            M, N, K, int(epilogue), _p(bias), _p(aux), aux.stride(0) if aux is not None else 0, _p(out2), float(p_drop),
+            int(seed) & 0xFFFFFFFF, _stream())
     ctx.check(rc)
     return out
 
@@ -89,9 +128,10 @@ def pack_batch(ids, seg_ids=None, kind="bert", lens_host=None):
     pk.seq_of = torch.empty(cap, dtype=torch.int32, device=dev)
     pk.key_valid = torch.empty(cap, dtype=torch.uint8, device=dev)
     ctx = _ctx(ids)
-    ctx.check(_lib.lib().nbest_pack_batch(ctx.handle, _p(ids), _p(seg_ids), B, S, 1 if kind == "xlm-roberta" else 0,
-                                          _p(pk.lens), _p(pk.cu_seqlens), _p(pk.tokens), _p(pk.seg), _p(pk.pos),
-                                          _p(pk.seq_of), _p(pk.key_valid), _stream()))
+    with _Timed('pack_batch', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_pack_batch(ctx.handle, _p(ids), _p(seg_ids), B, S, 1 if kind == "xlm-roberta" else 0,
+                                              _p(pk.lens), _p(pk.cu_seqlens), _p(pk.tokens), _p(pk.seg), _p(pk.pos),
+                                              _p(pk.seq_of), _p(pk.key_valid), _stream()))
     if lens_host is not None and kind != "xlm-roberta":
         pk.T = int(sum(lens_host))
         pk.max_len = int(max(lens_host))
@@ -105,56 +145,64 @@ def pack_batch(ids, seg_ids=None, kind="bert", lens_host=None):
 # ---------------------------------------------------------------------------------------------------------- embed / LN
 def embed_ln_fwd(pk, word, posemb, type_emb, gamma, beta, eps, y, mean, rstd, p_drop=0.0, seed=0):
     ctx = _ctx(word)
-    ctx.check(_lib.lib().nbest_embed_ln_fwd(ctx.handle, _p(pk.tokens), _p(pk.seg), _p(pk.pos), pk.T, _p(word), _p(posemb),
-                                            _p(type_emb), _p(gamma), _p(beta), float(eps), word.shape[1], _p(y), _p(mean),
-                                            _p(rstd), float(p_drop), _seed(seed), _stream()))
+    with _Timed('embed_ln_fwd', 0.0, pk.T * (3 * 768 * 4 + 768 * 2.0)):
+        ctx.check(_lib.lib().nbest_embed_ln_fwd(ctx.handle, _p(pk.tokens), _p(pk.seg), _p(pk.pos), pk.T, _p(word), _p(posemb),
+                                                _p(type_emb), _p(gamma), _p(beta), float(eps), word.shape[1], _p(y), _p(mean),
+                                                _p(rstd), float(p_drop), _seed(seed), _stream()))
 
 
 def embed_ln_bwd(pk, word, posemb, type_emb, gamma, mean, rstd, dy, dword, dpos, dtype, dgamma, dbeta, p_drop=0.0, seed=0,
                  word_pad_row=-1, pos_pad_row=-1, T=None):
     ctx = _ctx(word)
-    ctx.check(_lib.lib().nbest_embed_ln_bwd(ctx.handle, _p(pk.tokens), _p(pk.seg), _p(pk.pos), pk.T if T is None else T,
-                                            _p(word), _p(posemb), _p(type_emb), _p(gamma), _p(mean), _p(rstd), word.shape[1],
-                                            _p(dy), float(p_drop), _seed(seed), _p(dword), _p(dpos), _p(dtype), _p(dgamma),
-                                            _p(dbeta), int(word_pad_row), int(pos_pad_row), _stream()))
+    with _Timed('embed_ln_bwd', 0.0, (pk.T if T is None else T) * (3 * 768 * 4 + 768 * 2 + 3 * 768 * 4.0)):
+        ctx.check(_lib.lib().nbest_embed_ln_bwd(ctx.handle, _p(pk.tokens), _p(pk.seg), _p(pk.pos), pk.T if T is None else T,
+                                                _p(word), _p(posemb), _p(type_emb), _p(gamma), _p(mean), _p(rstd), word.shape[1],
+                                                _p(dy), float(p_drop), _seed(seed), _p(dword), _p(dpos), _p(dtype), _p(dgamma),
+                                                _p(dbeta), int(word_pad_row), int(pos_pad_row), _stream()))
 
 
 def ln_fwd(x, gamma, beta, eps, y, mean=None, rstd=None, T=None):
     ctx = _ctx(x)
-    ctx.check(_lib.lib().nbest_ln_fwd(ctx.handle, _p(x), _p(gamma), _p(beta), float(eps), x.shape[0] if T is None else T,
-                                      x.shape[1], _p(y), _p(mean), _p(rstd), _stream()))
+    with _Timed('ln_fwd', 0.0, (x.shape[0] if T is None else T) * (2 * 768 * 2.0)):
+        ctx.check(_lib.lib().nbest_ln_fwd(ctx.handle, _p(x), _p(gamma), _p(beta), float(eps), x.shape[0] if T is None else T,
+                                          x.shape[1], _p(y), _p(mean), _p(rstd), _stream()))
 
 
 def ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dx_masked=None, dbias=None, p_drop=0.0, seed=0, T=None):
     ctx = _ctx(x)
-    ctx.check(_lib.lib().nbest_ln_bwd(ctx.handle, _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma),
-                                      x.shape[0] if T is None else T, x.shape[1], _p(dx), _p(dx_masked), float(p_drop),
-                                      _seed(seed), _p(dgamma), _p(dbeta), _p(dbias), _stream()))
+    with _Timed('ln_bwd', 0.0, (x.shape[0] if T is None else T) * ((3 + (dx_masked is not None)) * 768 * 2.0)):
+        ctx.check(_lib.lib().nbest_ln_bwd(ctx.handle, _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma),
+                                          x.shape[0] if T is None else T, x.shape[1], _p(dx), _p(dx_masked), float(p_drop),
+                                          _seed(seed), _p(dgamma), _p(dbeta), _p(dbias), _stream()))
 
 
 def colsum(x, out, T=None):
     ctx = _ctx(x)
-    ctx.check(_lib.lib().nbest_colsum_bf16(ctx.handle, _p(x), x.shape[0] if T is None else T, x.shape[1], _p(out), _stream()))
+    with _Timed('colsum_bf16', 0.0, (x.shape[0] if T is None else T) * x.shape[1] * 2.0):
+        ctx.check(_lib.lib().nbest_colsum_bf16(ctx.handle, _p(x), x.shape[0] if T is None else T, x.shape[1], _p(out), _stream()))
 
 
 def cast_f32_bf16(src, dst):
     ctx = _ctx(src)
-    ctx.check(_lib.lib().nbest_cast_f32_bf16(ctx.handle, _p(src), _p(dst), src.numel(), _stream()))
+    with _Timed('cast_f32_bf16', 0.0, src.numel() * 6.0):
+        ctx.check(_lib.lib().nbest_cast_f32_bf16(ctx.handle, _p(src), _p(dst), src.numel(), _stream()))
 
 
 # ---------------------------------------------------------------------------------------------------------- attention
 def attn_fwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out, lse, p_drop=0.0, seed=0):
     ctx = _ctx(qkv)
-    ctx.check(_lib.lib().nbest_attn_varlen_fwd(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
-                                               _p(out), _p(lse), float(p_drop), _seed(seed), _stream()))
+    with _Timed('attn_varlen_fwd', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_attn_varlen_fwd(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
+                                                   _p(out), _p(lse), float(p_drop), _seed(seed), _stream()))
 
 
 def attn_bwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out, dout, lse, dqkv, delta_ws, p_drop=0.0, seed=0,
              T_active=None):
     ctx = _ctx(qkv)
-    ctx.check(_lib.lib().nbest_attn_varlen_bwd(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
-                                               T if T_active is None else T_active, _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta_ws), float(p_drop), _seed(seed),
-                                               _stream()))
+    with _Timed('attn_varlen_bwd', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_attn_varlen_bwd(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
+                                                   T if T_active is None else T_active, _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta_ws), float(p_drop), _seed(seed),
+                                                   _stream()))
 
 
 # ---------------------------------------------------------------------------------------------------------- STC head / loss
@@ -178,6 +226,7 @@ class DeviceHierarchy:
             col_group += [g] * len(t2b[k])
             col_bottom += t2b[k]
         none_set = set(int(x) for x in none_bottoms)
+        self.none_bottoms = none_set
         none_col = [1 if (c >= self.n_top and col_bottom[c] in none_set) else 0 for c in range(self.n_cols)]
         self.grp_off_host, self.col_bottom_host = grp_off, col_bottom
         i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=device)
@@ -195,41 +244,47 @@ class DeviceHierarchy:
 
 def stc_head_fwd(x, cu_seqlens, B, W, bias, hier, cls, logits, top, bottom, final, decode=None, p_drop=0.0, seed=0):
     ctx = _ctx(x)
-    ctx.check(_lib.lib().nbest_stc_head_fwd(ctx.handle, _p(x), _p(cu_seqlens), B, x.shape[1], _p(W), _p(bias), hier.ref(),
-                                            _p(hier.none_col), float(p_drop), _seed(seed), _p(cls), _p(logits), _p(top),
-                                            _p(bottom), _p(final), _p(decode), _stream()))
+    with _Timed('stc_head_fwd', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_stc_head_fwd(ctx.handle, _p(x), _p(cu_seqlens), B, x.shape[1], _p(W), _p(bias), hier.ref(),
+                                                _p(hier.none_col), float(p_drop), _seed(seed), _p(cls), _p(logits), _p(top),
+                                                _p(bottom), _p(final), _p(decode), _stream()))
 
 
 def stc_loss_fwd_bwd(logits, labels, hier, losses, dlogits, asr_cls=None, trans_cls=None, mse_scale=1.0, d_asr=None,
                      d_trans=None):
     ctx = _ctx(logits)
-    ctx.check(_lib.lib().nbest_stc_loss_fwd_bwd(ctx.handle, _p(logits), _p(labels), logits.shape[0], hier.ref(), _p(asr_cls),
-                                                _p(trans_cls), asr_cls.shape[1] if asr_cls is not None else 768,
-                                                float(mse_scale), _p(losses), _p(dlogits), _p(d_asr), _p(d_trans), _stream()))
+    with _Timed('stc_loss_fwd_bwd', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_stc_loss_fwd_bwd(ctx.handle, _p(logits), _p(labels), logits.shape[0], hier.ref(), _p(asr_cls),
+                                                    _p(trans_cls), asr_cls.shape[1] if asr_cls is not None else 768,
+                                                    float(mse_scale), _p(losses), _p(dlogits), _p(d_asr), _p(d_trans), _stream()))
 
 
 def stc_scores_bwd(top, bottom, d_top, d_bottom, d_final, hier, dlogits):
     ctx = _ctx(top)
-    ctx.check(_lib.lib().nbest_stc_scores_bwd(ctx.handle, _p(top), _p(bottom), _p(d_top), _p(d_bottom), _p(d_final),
-                                              top.shape[0], hier.ref(), _p(dlogits), _stream()))
+    with _Timed('stc_scores_bwd', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_stc_scores_bwd(ctx.handle, _p(top), _p(bottom), _p(d_top), _p(d_bottom), _p(d_final),
+                                                  top.shape[0], hier.ref(), _p(dlogits), _stream()))
 
 
 def stc_head_bwd(dlogits, cls, W, hier, dW, dbias, dcls, accumulate_dcls=False, p_drop=0.0, seed=0):
     ctx = _ctx(cls)
-    ctx.check(_lib.lib().nbest_stc_head_bwd(ctx.handle, _p(dlogits), _p(cls), _p(W), cls.shape[0], cls.shape[1], hier.ref(),
-                                            float(p_drop), _seed(seed), _p(dW), _p(dbias), _p(dcls), int(accumulate_dcls),
-                                            _stream()))
+    with _Timed('stc_head_bwd', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_stc_head_bwd(ctx.handle, _p(dlogits), _p(cls), _p(W), cls.shape[0], cls.shape[1], hier.ref(),
+                                                float(p_drop), _seed(seed), _p(dW), _p(dbias), _p(dcls), int(accumulate_dcls),
+                                                _stream()))
 
 
 def cls_scatter(dcls, cu_seqlens, B, T, dx):
     ctx = _ctx(dcls)
-    ctx.check(_lib.lib().nbest_cls_scatter(ctx.handle, _p(dcls), _p(cu_seqlens), B, T, dcls.shape[1], _p(dx), _stream()))
+    with _Timed('cls_scatter', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_cls_scatter(ctx.handle, _p(dcls), _p(cu_seqlens), B, T, dcls.shape[1], _p(dx), _stream()))
 
 
 # ---------------------------------------------------------------------------------------------------------- BertAdam
 def bertadam_step(p, g, m, v, p_bf16, tensors_dev, n_tensors, chunks_dev, n_chunks, norms_ws, sched, b1=0.9, b2=0.999,
                   eps=1e-6, max_grad_norm=1.0):
     ctx = _ctx(p)
-    ctx.check(_lib.lib().nbest_bertadam_step(ctx.handle, _p(p), _p(g), _p(m), _p(v), _p(p_bf16), _p(tensors_dev), n_tensors,
-                                             _p(chunks_dev), n_chunks, _p(norms_ws), float(sched), float(b1), float(b2),
-                                             float(eps), float(max_grad_norm), _stream()))
+    with _Timed('bertadam_step', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_bertadam_step(ctx.handle, _p(p), _p(g), _p(m), _p(v), _p(p_bf16), _p(tensors_dev), n_tensors,
+                                                 _p(chunks_dev), n_chunks, _p(norms_ws), float(sched), float(b1), float(b2),
+                                                 float(eps), float(max_grad_norm), _stream()))

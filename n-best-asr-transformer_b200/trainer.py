@@ -1,0 +1,138 @@
+"""Data-parallel trainer: one process per GPU, bucketed NCCL gradient all-reduce overlapped with backward.
+
+Replaces the reference's single-GPU picker (utils/gpu_selection.py:27-66, n_best_asr_bert.py:116-126) — the only place
+the path shards. Utterances are independent through forward/backward, weights are replicated, and there
+is exactly one exchange per optimizer step: the SUM of the flat fp32 gradient buffer over ranks.
+
+Parity-critical details:
+  * the BCE / CE terms are sum-reduced over the batch (n_best_asr_bert.py:572-573) -> gradients are SUMMED, no 1/R;
+  * the MSE term is a mean over B*768 (n_best_asr_bert.py:574) -> each rank scales it by 1/R (mse_scale);
+  * BertAdam clips per tensor (models/optimization.py:270-271) -> the norm pass runs AFTER the all-reduce;
+  * the pooler never receives gradients -> it is not in any bucket.
+Buckets are contiguous slices of the flat gradient buffer in the order backward finishes them (head, layer L-1 ... 0,
+embeddings); each is all-reduced on a side stream as soon as its last wgrad kernel has been enqueued.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+class GradBucketer:
+    """Contiguous gradient buckets over a flat buffer + their (optionally asynchronous) SUM all-reduce.
+
+    `segments` is a list of (name, start, end) element ranges of the flat gradient buffer, in the order backward
+    completes them. Works on CPU tensors with the gloo backend as well (used by the world_size-2 tests).
+    """
+
+    def __init__(self, flat_grads, segments, group=None, comm_stream=None):
+        self.flat = flat_grads
+        self.segments = list(segments)
+        self.by_name = {n: (s, e) for n, s, e in self.segments}
+        self.group = group
+        self.comm_stream = comm_stream
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self._pending = []
+
+    def reduce(self, name):
+        """Enqueue the all-reduce of one bucket. CUDA: on the comm stream, after everything enqueued so far on the
+        current stream; CPU (gloo): asynchronous work handle."""
+        if self.world == 1:
+            return
+        s, e = self.by_name[name]
+        buf = self.flat[s:e]
+        if buf.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self._pending.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def wait(self):
+        """Make the current stream (or the host, for gloo) wait for every enqueued bucket."""
+        if self.world == 1:
+            return
+        if self.flat.is_cuda:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+
+
+def model_segments(model):
+    """Bucket plan for a TOD_ASR_Transformer_STC: head | layer L-1 | ... | layer 0 | embeddings (pooler excluded)."""
+    f, idx = model.flat, model._index
+    names = model._names
+
+    def span(first, last):
+        i0, i1 = idx[first], idx[last]
+        end = f.offsets[i1] + int(torch.Size(f.shapes[i1]).numel())
+        return f.offsets[i0], end
+
+    segs = []
+    head_first = "clf.top_linear_layer.weight"
+    segs.append(("head",) + span(head_first, names[-1]))
+    for l in reversed(range(model.spec.layers)):
+        p = "bert_encoder.encoder.layer.%d." % l
+        segs.append(("layer%d" % l,) + span(p + "attention.self.query.weight", p + "output.LayerNorm.bias"))
+    e = "bert_encoder.embeddings."
+    segs.append(("emb",) + span(e + "word_embeddings.weight", e + "LayerNorm.bias"))
+    return segs
+
+
+def init_distributed():
+    """torchrun-style bootstrap (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if torch.cuda.is_available():
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo", rank=rank, world_size=world)
+    return rank, local, world
+
+
+class DataParallelTrainer:
+    """Fused training step on one rank of a data-parallel job.
+
+        trainer = DataParallelTrainer(model, optimizer, add_l2_loss=False)
+        losses = trainer.step(ids, labels, trans_ids, seg, trans_seg)     # device tensor [mse, bce_final, bce_top, ce]
+
+    `losses` holds this rank's local terms (sum-reduced over its own utterances); `global_losses()` all-reduces them
+    for logging (once per logging interval, not per step)."""
+
+    def __init__(self, model, optimizer, add_l2_loss=False, group=None):
+        self.model, self.optimizer, self.add_l2_loss = model, optimizer, add_l2_loss
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.comm_stream = torch.cuda.Stream(device=model.device) if self.world > 1 else None
+        self.bucketer = GradBucketer(model.flat.grads, model_segments(model), group, self.comm_stream)
+        self.group = group
+
+    def step(self, ids, labels, trans_ids=None, seg=None, trans_seg=None, lens=None, trans_lens=None):
+        m = self.model
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())     # zeroed grads / previous step are visible
+        m._grad_ready_hook = self.bucketer.reduce if self.world > 1 else None
+        try:
+            losses, head = m.forward_loss_backward(ids, labels, trans_ids, seg, trans_seg, add_l2_loss=self.add_l2_loss,
+                                                   mse_scale=1.0 / self.world, input_lens=lens, trans_input_lens=trans_lens)
+        finally:
+            m._grad_ready_hook = None
+        self.bucketer.wait()
+        self.optimizer.step()
+        self.optimizer.zero_grad()
+        self.last_head = head
+        return losses
+
+    def global_losses(self, losses):
+        if self.world > 1:
+            losses = losses.clone()
+            dist.all_reduce(losses, op=dist.ReduceOp.SUM, group=self.group)
+        return losses
