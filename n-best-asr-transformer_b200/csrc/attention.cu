@@ -395,8 +395,8 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restr
 }
 
 inline uint32_t drop_threshold(float p) {
-  double t = (double)p * 4294967296.0;
-  return p <= 0.f ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+  const double t = (double)p * 65536.0 + 0.5;   // 16-bit threshold (ptx.cuh dropout_keep)
+  return p <= 0.f ? 0u : (t >= 65535.0 ? 65535u : (uint32_t)t);
 }
 
 }  // namespace

@@ -21,8 +21,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
 __device__ __forceinline__ float4 bf16x4_to_f4(uint2 u) { return make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y)); }
 __device__ __forceinline__ uint2 f4_to_bf16x4(float4 v) { return make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)); }
 static inline uint32_t drop_threshold(float p) {
-  double t = (double)p * 4294967296.0;
-  return p <= 0.f ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+  const double t = (double)p * 65536.0 + 0.5;   // 16-bit threshold (ptx.cuh dropout_keep)
+  return p <= 0.f ? 0u : (t >= 65535.0 ? 65535u : (uint32_t)t);
 }
 
 // ------------------------------------------------------------------------------------------------ packing

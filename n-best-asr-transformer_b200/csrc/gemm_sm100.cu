@@ -5,8 +5,8 @@
 // BertIntermediate.dense + GELU (:339-342), BertOutput.dense (:352-356), and their autograd products
 // (dgrad / wgrad of n_best_asr_bert.py:264 `total_loss.backward()`).
 //
-// One CTA per SM (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
-// warps 2..5 = epilogue (one TMEM lane quarter each). Tiles are 128 x BN (BN = 256 or 128) x 64, the smem ring has
+// One CTA per SM (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
+// warps 2..9 = epilogue (two warps per TMEM lane quarter, splitting the tile's column chunks). Tiles are 128 x BN (BN = 256 or 128) x 64, the smem ring has
 // 4 (BN=256) or 6 (BN=128) stages of 128-byte-swizzled operand tiles, and the fp32 accumulator is double buffered
 // in TMEM (2*BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
@@ -22,8 +22,9 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
 constexpr int kEpiWarp0 = 2;
+constexpr int kEpiWarps = 8;   // two per TMEM lane quarter: they split the tile's 32-column chunks (even / odd)
+constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
 constexpr uint32_t kChunkBytes = 64 * BK * 2;  // one 64-row (or 64-col) x 64 bf16 box = 8 KiB
 
 struct GemmArgs {
@@ -46,7 +47,7 @@ struct Cfg {
   static constexpr uint32_t kABytes = BM * BK * 2;
   static constexpr uint32_t kBBytes = BN * BK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kStagingBytes = 4 * 2048;  // 4 epilogue warps x (32 rows x 64 B)
+  static constexpr uint32_t kStagingBytes = kEpiWarps * 2048;  // per epilogue warp: 32 rows x 64 B
   static constexpr uint32_t kBarOffset = kStages * kStageBytes + kStagingBytes;
   static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;  // + barriers + alignment slack
   static constexpr uint32_t kTmemCols = 2 * BN;
@@ -85,7 +86,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -174,6 +175,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------------------------------------------ epilogue (4 warps, one TMEM lane quarter each)
     const int q = warp & 3;  // tcgen05.ld: warp w may only touch lanes [32*(w%4), 32*(w%4)+32)
     uint8_t* st = staging + (warp - kEpiWarp0) * 2048;
+    const int c_first = (warp - kEpiWarp0) >> 2;  // this warp handles chunks c_first, c_first + 2, ...
     const uint32_t st_u32 = smem_u32(st);
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
@@ -191,13 +193,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int i = 0; i < 4; ++i) {
           const int gr = m0 + q * 32 + i * 8 + crow;
           aux_next[i] = make_uint4(0, 0, 0, 0);
-          if (gr < g.M) aux_next[i] = __ldg(reinterpret_cast<const uint4*>(g.aux + (int64_t)gr * g.ldaux + n0 + cseg * 8));
+          if (gr < g.M)
+            aux_next[i] = __ldg(reinterpret_cast<const uint4*>(g.aux + (int64_t)gr * g.ldaux + n0 + c_first * 32 + cseg * 8));
         }
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_first; c < BN / 32; c += 2) {
         const int nc = n0 + c * 32;
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + c * 32, r);
@@ -206,13 +209,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<uint4*>(st + stage_off(i * 8 + crow, cseg)) = aux_next[i];
-          if (c + 1 < BN / 32) {
+          if (c + 2 < BN / 32) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int gr = m0 + q * 32 + i * 8 + crow;
               aux_next[i] = make_uint4(0, 0, 0, 0);
               if (gr < g.M)
-                aux_next[i] = __ldg(reinterpret_cast<const uint4*>(g.aux + (int64_t)gr * g.ldaux + nc + 32 + cseg * 8));
+                aux_next[i] = __ldg(reinterpret_cast<const uint4*>(g.aux + (int64_t)gr * g.ldaux + nc + 64 + cseg * 8));
             }
           }
           __syncwarp();
@@ -274,7 +277,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (g.drop_thresh != 0) {
               const uint32_t base = (uint32_t)row * (uint32_t)g.N + (uint32_t)nc;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = dropout_keep(g.seed, base + j, g.drop_thresh) ? v[j] * g.drop_scale : 0.f;
+              for (int j = 0; j < 32; j += 2) {
+                bool k0, k1;
+                dropout_keep2(g.seed, base + j, g.drop_thresh, k0, k1);   // base is even (N and nc are even)
+                v[j] = k0 ? v[j] * g.drop_scale : 0.f;
+                v[j + 1] = k1 ? v[j + 1] * g.drop_scale : 0.f;
+              }
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -415,8 +423,8 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
   g.out2 = reinterpret_cast<__nv_bfloat16*>(out2_bf16);
   g.seed = seed;
   if (p_drop > 0.f) {
-    double t = (double)p_drop * 4294967296.0;
-    g.drop_thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    const double t = (double)p_drop * 65536.0 + 0.5;   // 16-bit threshold (ptx.cuh dropout_keep)
+    g.drop_thresh = t >= 65535.0 ? 65535u : (uint32_t)t;
     g.drop_scale = 1.0f / (1.0f - p_drop);
   } else {
     g.drop_thresh = 0;

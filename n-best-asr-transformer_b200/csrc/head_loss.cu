@@ -353,8 +353,8 @@ __global__ void cls_scatter_kernel(const float* __restrict__ dcls, const int32_t
 }
 
 inline uint32_t drop_threshold(float p) {
-  double t = (double)p * 4294967296.0;
-  return p <= 0.f ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+  const double t = (double)p * 65536.0 + 0.5;   // 16-bit threshold (ptx.cuh dropout_keep)
+  return p <= 0.f ? 0u : (t >= 65535.0 ? 65535u : (uint32_t)t);
 }
 
 int check_hier(nbest_ctx* ctx, const nbest_hierarchy* h, Hier* out) {
