@@ -36,7 +36,7 @@ def _pieces(rng, words):
 def synth_batch(kind, vocab_size, hier, B, n_hyps=5, max_len=128, seed=999, with_trans=True, dense=False):
     """Returns dict(ids, seg, lens, [trans_ids, trans_seg, trans_lens,] labels) of CPU tensors / lists.
 
-    `hier` needs .n_top, .n_bottom, .top2bottom and .none_bottoms (oracle Hierarchy or ops.DeviceHierarchy-like).
+    `hier` needs .n_top, .n_bottom, .top2bottom and .none_bottoms (e.g. ops.DeviceHierarchy).
     dense=True makes every ASR sequence exactly max_len tokens (the worst case quoted for the roofline)."""
     rng = np.random.RandomState(seed)
     if kind == "xlm-roberta":

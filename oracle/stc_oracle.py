@@ -408,4 +408,5 @@ def train_step(params, cfg, hier, batch, opt_state, hp, drop=None):
     if opt_state is not None:
         with torch.no_grad():
             bertadam_step(params, grads, opt_state, hp["lr"], hp["bert_lr"], hp["warmup"], hp["t_total"])
-    return dict(total=float(total), **{k: float(v) for k, v in terms.items()}), grads, (top, bottoms, final, asr, trans)
+    return (dict(total=float(total.detach()), **{k: float(v.detach()) for k, v in terms.items()}), grads,
+            (top, bottoms, final, asr, trans))

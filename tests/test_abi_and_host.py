@@ -1,0 +1,140 @@
+"""CPU: the C-ABI library loads and exports every symbol include/nbest_sm100.h declares (no compute calls), and the
+host-side logic (optimizer tables, schedules, flat layout, bucket plan, synthetic generator, no-fallback behaviour)."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _declared_symbols():
+    header = open(os.path.join(ROOT, "include", "nbest_sm100.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    return sorted(set(re.findall(r"\b(nbest_[a-z0-9_]+)\s*\(", header)))
+
+
+def test_library_exports_every_declared_symbol():
+    from nbest_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "run `python n-best-asr-transformer_b200/build.py` (or __graft_entry__.build())"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "libnbest_sm100.so does not export %s" % name
+    assert sorted(_lib.exported_symbols()) == declared, "ctypes signature table and header disagree"
+    lib.nbest_abi_version.restype = ctypes.c_int
+    assert lib.nbest_abi_version() == 1
+
+
+def test_header_cites_reference_for_every_entry_point():
+    header = open(os.path.join(ROOT, "include", "nbest_sm100.h")).read()
+    for frag in ("models/model.py", "utils/bert_xlnet_inputs.py", "models/optimization.py", "hierarchical_classifier.py",
+                 "n_best_asr_bert.py", "modeling_bert.py", "utils/gpu_selection.py"):
+        assert frag in header, frag
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_no_cpu_fallback():
+    """Without a GPU the product refuses to run instead of silently computing somewhere else."""
+    from nbest_b200 import _lib, ops
+    from nbest_b200.model import EncoderSpec, TOD_ASR_Transformer_STC
+    with pytest.raises(_lib.NbestError):
+        _lib.Context(0)
+    with pytest.raises(RuntimeError):
+        ops.gemm(torch.zeros(128, 64, dtype=torch.bfloat16), torch.zeros(128, 64, dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError):
+        TOD_ASR_Transformer_STC(spec=EncoderSpec.bert_base(layers=1), top2bottom={0: [0], 1: [1, 2]}, dropout=0.0, device="cpu")
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "n-best-asr-transformer_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle|import_module\(.oracle|oracle\.", src, flags=re.M), \
+                fn + " imports the oracle"
+
+
+def test_schedule_matches_reference_formula():
+    from nbest_b200.optim import schedule_multiplier
+    from oracle import stc_oracle as O
+    for t_total, warm in ((2300, 0.1), (8, 0.1), (50, 0.25)):
+        for step in range(0, t_total + 5):
+            assert schedule_multiplier(step, t_total, warm) == O.warmup_linear(step, t_total, warm)
+    assert schedule_multiplier(0, 2300, 0.1) == 0.0                       # the first update has lr 0
+    assert schedule_multiplier(7, -1, 0.1) == 1.0
+
+
+def test_flat_layout_alignment_and_fused_views():
+    from nbest_b200.optim import FlatBuffers
+    shapes = [(30, 768), (75, 768), (30,), (75,), (27,), (768,)]
+    fb = FlatBuffers(shapes, "cpu", with_bf16=False, aligns=[64, 64, 64, 1, 1, 64])
+    assert fb.offsets[0] == 0 and fb.offsets[1] == 30 * 768                # weights contiguous: fused [105,768] view
+    assert fb.offsets[3] == fb.offsets[2] + 30 and fb.offsets[4] == fb.offsets[3] + 75     # packed biases: [132] vector
+    assert fb.offsets[5] % 64 == 0 and fb.total % 64 == 0
+    fb.view(fb.params, 3).fill_(2.0)
+    assert float(fb.params[fb.offsets[2]:fb.offsets[2] + 132].sum()) == 150.0
+
+
+def test_adam_tables_cover_active_tensors_exactly():
+    from nbest_b200.optim import build_adam_tables
+    spec = [dict(offset=0, numel=100000, lr=1e-3, weight_decay=0.01, active=True),
+            dict(offset=100032, numel=4096, lr=1e-3, weight_decay=0.0, active=False),
+            dict(offset=104128, numel=30, lr=2e-3, weight_decay=0.0, active=True),
+            dict(offset=104158, numel=75, lr=2e-3, weight_decay=0.0, active=True)]
+    t = build_adam_tables(spec, "cpu", chunk=16384)
+    ch = t["chunks"].numpy()
+    assert set(ch[:, 0].tolist()) == {0, 2, 3}
+    for i, s in enumerate(spec):
+        rows = ch[ch[:, 0] == i]
+        if not s["active"]:
+            assert len(rows) == 0
+            continue
+        assert rows[:, 2].sum() == s["numel"] and rows[0, 1] == 0
+        assert (rows[1:, 1] == np.cumsum(rows[:-1, 2])).all()
+    assert t["tensors"].numel() == 4 * ctypes.sizeof(__import__("nbest_b200._lib", fromlist=["AdamTensor"]).AdamTensor)
+
+
+def test_synthetic_generator_matches_dstc2_shape_statistics():
+    from nbest_b200.synth import synth_batch
+    from oracle import stc_oracle as O
+    hj = json.load(open(os.path.join(GOLD, "dstc2_hierarchy.json")))
+    hier = O.Hierarchy({int(k): v for k, v in hj["top2bottom"].items()}, hj["none_bottoms"])
+    b = synth_batch("bert", 30522, hier, 4096, 5, 128, seed=1)
+    L = np.array(b["lens"])
+    assert 43 < L.mean() < 50 and L.max() <= 128 and L.min() >= 8          # mean 46.3
+    ids, seg = b["ids"].numpy(), b["seg"].numpy()
+    assert (ids[:, 0] == 101).all()
+    for r in range(64):
+        row, sg = ids[r, :L[r]], seg[r, :L[r]]
+        fs = int(np.argmax(row == 102))
+        assert (sg[:fs] == 0).all() and (sg[fs:] == 1).all() and (ids[r, L[r]:] == 0).all()
+    lab = b["labels"].numpy()
+    assert 1.2 < lab.sum(1).mean() < 1.45                                   # 1.32 labels / utterance
+    none_cols = sorted(hier.none_bottoms)
+    assert lab[:, none_cols].sum() == 0                                     # a gold label is never a NONE label
+    for k in hier.group_tops:
+        assert (lab[:, hier.top2bottom[k]].sum(1) <= 1).all()               # STC_util.py:34 invariant
+    x = synth_batch("xlm-roberta", 250002, hier, 8, 5, 128, seed=2)
+    assert (x["ids"][:, 0] == 0).all() and int(x["ids"].max()) < 250002
+    d = synth_batch("bert", 30522, hier, 8, 5, 128, seed=3, dense=True)
+    assert d["lens"] == [128] * 8
+
+
+def test_hierarchy_tables_are_consistent():
+    from oracle import stc_oracle as O
+    hj = json.load(open(os.path.join(GOLD, "dstc2_hierarchy.json")))
+    hier = O.Hierarchy({int(k): v for k, v in hj["top2bottom"].items()}, hj["none_bottoms"])
+    assert (hier.n_top, hier.n_bottom, hier.n_groups, hier.n_cols) == (30, 161, 10, 171)
+    assert [len(hier.top2bottom[k]) for k in hier.group_tops] == [75, 27, 4, 5, 7, 6, 4, 7, 4, 2]
+    scored = [b for b in hier.col_bottom if b >= 0]
+    assert sorted(scored) == list(range(161))                                # every bottom label scored exactly once
+    assert sum(hier.none_col) == 10                                          # one NONE value per multi-way group
+    for g in range(hier.n_groups):
+        assert hier.none_col[hier.grp_off[g + 1] - 1] == 1                   # ... and it is the group's last column
