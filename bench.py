@@ -164,6 +164,8 @@ def main():
     from nbest_b200.synth import synth_batch
     from nbest_b200.trainer import DataParallelTrainer, init_distributed
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NBEST_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL banners go to stdout; stdout carries exactly one JSON line
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU port)")
     rank, local, world = init_distributed()

@@ -106,7 +106,7 @@ __device__ __forceinline__ void zero_acc(float (&a)[8][4]) {
 __device__ __forceinline__ uint32_t pidx(int h, int T, int tq, int j) { return ((uint32_t)h * (uint32_t)T + (uint32_t)tq) * 512u + (uint32_t)j; }
 
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu, const uint8_t* __restrict__ key_valid,
                 int heads, int T, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, float scale, uint32_t thr,
                 float rscale, uint32_t seed) {
@@ -236,7 +236,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
 // One CTA per (key block, head, sequence); warp w owns keys [16w, 16w+16) of the block. Works on S^T = K Q^T so that
 // P^T / dS^T come out of the MMA already in A-fragment layout for the dV = P^T dO and dK = dS^T Q products.
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
                      const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
                      const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
@@ -321,7 +321,7 @@ attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __res
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dQ
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
                    const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,

@@ -103,8 +103,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------------------------------------------ TMA producer
     uint32_t stage = 0, phase = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-      const int split = w % g.num_splits;
-      const int tile = w / g.num_splits;
+      const int num_tiles = g.num_m_tiles * g.num_n_tiles;   // tile fastest: concurrent CTAs share one T-range (L2 reuse)
+      const int split = w / num_tiles;
+      const int tile = w % num_tiles;
       const int m0 = (tile / g.num_n_tiles) * BM;
       const int n0 = (tile % g.num_n_tiles) * BN;
       const int kb0 = split * g.kb_per_split;
@@ -142,7 +143,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr uint32_t a_kstep = A_MN ? 2048 : 32, b_kstep = B_MN ? 2048 : 32;  // bytes per UMMA_K = 16
     uint32_t stage = 0, phase = 0, it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-      const int split = w % g.num_splits;
+      const int split = w / (g.num_m_tiles * g.num_n_tiles);
       const int kb0 = split * g.kb_per_split;
       const int kb1 = min(kb0 + g.kb_per_split, g.num_kb);
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -179,7 +180,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t st_u32 = smem_u32(st);
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-      const int tile = w / g.num_splits;
+      const int tile = w % (g.num_m_tiles * g.num_n_tiles);
       const int m0 = (tile / g.num_n_tiles) * BM;
       const int n0 = (tile % g.num_n_tiles) * BN;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;

@@ -226,31 +226,19 @@ def packing_case(prepare_inputs_for_roberta, m):
     """A2 golden: the reference's own prepare_inputs_for_roberta on real lines of the shipped `valid` file with a
     deterministic fake tokenizer (no vocabularies exist offline) -> padded tensors the packed layout must invert."""
 
-    class FakeTok:
-        cls_token, sep_token, pad_token_id = "[CLS]", "[SEP]", 0
-
-        def tokenize(self, w):                                               # 1-3 deterministic word pieces
-            if w in ("[SEP]", "[CLS]"):
-                return [w]
-            n = 1 + (sum(map(ord, w)) % 3 if len(w) > 4 else 0)
-            return [w] if n == 1 else [w[:2]] + ["##" + w[2 + i:3 + i] for i in range(n - 1)]
-
-        def convert_tokens_to_ids(self, toks):
-            sp = {"[CLS]": 101, "[SEP]": 102}
-            return [sp.get(t, 1000 + (hash_str(t) % 29000)) for t in toks]
-
-    def hash_str(s):
-        h = 2166136261
-        for ch in s.encode():
-            h = ((h ^ ch) * 16777619) & 0xFFFFFFFF
-        return h
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fake_tokenizer import FakeTok, FakeXlmrTok
 
     lines = open(os.path.join(REF, "dstc2_data/processed_data/raw/valid")).read().strip().split("\n")[:24]
     raw_in = [l.split("\t<=>\t")[0].strip().split(" ") for l in lines]
     out = {}
-    for tag, kw in (("default", dict(without_system_act=False)), ("nosys", dict(without_system_act=True))):
-        opt = Namespace(tod_pre_trained_model=None, pre_trained_model="bert", **kw)
-        ids, seg, lens = prepare_inputs_for_roberta(raw_in, FakeTok(), opt, torch.device("cpu"))
+    cases = (("default", FakeTok(), dict(without_system_act=False, tod_pre_trained_model=None, pre_trained_model="bert")),
+             ("nosys", FakeTok(), dict(without_system_act=True, tod_pre_trained_model=None, pre_trained_model="bert")),
+             ("tod", FakeTok(), dict(without_system_act=False, tod_pre_trained_model="tod-bert", pre_trained_model=None)),
+             ("xlmr", FakeXlmrTok(), dict(without_system_act=False, tod_pre_trained_model=None, pre_trained_model="xlm-roberta")))
+    for tag, tok, kw in cases:
+        opt = Namespace(**kw)
+        ids, seg, lens = prepare_inputs_for_roberta(raw_in, tok, opt, torch.device("cpu"))
         out["ids_" + tag] = ids.numpy()
         out["lens_" + tag] = np.array(lens)
         if seg is not None:
