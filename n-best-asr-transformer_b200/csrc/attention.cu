@@ -62,13 +62,15 @@ __device__ __forceinline__ float quad_sum(float v) {
 }
 
 // acc[16 x 64] (8 n-tiles) = A(16 x 64 from tile rows row0..) * B^T where B tile is [n][k] (64 x 64).
-__device__ __forceinline__ void mma_a_tile_b_nk(float (&acc)[8][4], uint32_t sA, int row0, uint32_t sB, int lane) {
+// Only the first `npairs` 16-column pairs are computed (short sequences fill a fraction of the 64-wide tile).
+__device__ __forceinline__ void mma_a_tile_b_nk(float (&acc)[8][4], uint32_t sA, int row0, uint32_t sB, int lane, int npairs) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
     uint32_t a[4];
     lda(a, sA, row0, kk, lane);
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
+      if (np >= npairs) break;
       uint32_t b[4];
       ldb_nk(b, sB, np * 16, kk, lane);
       mma_bf16_16816(acc[2 * np], a, b[0], b[1]);
@@ -77,9 +79,11 @@ __device__ __forceinline__ void mma_a_tile_b_nk(float (&acc)[8][4], uint32_t sA,
   }
 }
 // acc[16 x 64] += P(16 x 64, fp32 accumulator layout, converted to bf16 A fragments) * B where B tile is [k][n].
-__device__ __forceinline__ void mma_p_b_kn(float (&acc)[8][4], const float (&p)[8][4], uint32_t sB, int lane) {
+// Only the first `nk` 16-row k-blocks contribute.
+__device__ __forceinline__ void mma_p_b_kn(float (&acc)[8][4], const float (&p)[8][4], uint32_t sB, int lane, int nk) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
+    if (kk >= nk) break;
     uint32_t a[4];
     a[0] = pack_bf16x2(p[2 * kk][0], p[2 * kk][1]);
     a[1] = pack_bf16x2(p[2 * kk][2], p[2 * kk][3]);
@@ -105,82 +109,112 @@ __device__ __forceinline__ void zero_acc(float (&a)[8][4]) {
 // dropout index of attention probability (head h, query token tq (global), key j inside the sequence)
 __device__ __forceinline__ uint32_t pidx(int h, int T, int tq, int j) { return ((uint32_t)h * (uint32_t)T + (uint32_t)tq) * 512u + (uint32_t)j; }
 
+// One CTA walks HPC heads of one (sequence, 64-row block): the tiles of iteration i+1 (next key block or next head)
+// are prefetched with cp.async into the other shared-memory stage while iteration i is computed, so the global-load
+// latency that dominates these short sequences is hidden inside the CTA instead of relying on occupancy.
+constexpr int kTile = BLK * D;   // elements of one 64 x 64 tile (8 KiB)
+
 // ------------------------------------------------------------------------------------------------ forward
+struct FwdSmem {
+  __nv_bfloat16 q[2][kTile], k[2][kTile], v[2][kTile];
+  uint8_t valid[2][BLK];
+};
+
+template <int HPC>
 __global__ void __launch_bounds__(kThreads, 4)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu, const uint8_t* __restrict__ key_valid,
                 int heads, int T, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, float scale, uint32_t thr,
                 float rscale, uint32_t seed) {
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qb = blockIdx.x, h0 = blockIdx.y * HPC, b = blockIdx.z;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   const int q0 = qb * BLK;
   if (q0 >= L) return;
-  __shared__ __align__(128) __nv_bfloat16 sQ[BLK * D], sK[BLK * D], sV[BLK * D];
-  __shared__ uint8_t sValid[BLK];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t ld = 3 * heads * D;
   const int hd = heads * D;
-  const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV);
-  load_tile(uQ, qkv + (int64_t)(s0 + q0) * ld + h * D, ld, L - q0);
-
-  float o[8][4];
-  zero_acc(o);
-  float m_i[2] = {-INFINITY, -INFINITY}, l_i[2] = {0.f, 0.f};
-  const float sl2 = scale * kLog2e;
-  uint32_t qf[4][4];
   const int nkb = (L + BLK - 1) / BLK;
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int k0 = kb * BLK;
-    load_tile(uK, qkv + (int64_t)(s0 + k0) * ld + hd + h * D, ld, L - k0);
-    load_tile(uV, qkv + (int64_t)(s0 + k0) * ld + 2 * hd + h * D, ld, L - k0);
-    cp_async_commit();
+  const int total = HPC * nkb;
+  const float sl2 = scale * kLog2e;
+
+  auto issue = [&](int it) {
+    const int hl = it / nkb, kb = it - hl * nkb, st = it & 1, h = h0 + hl, k0 = kb * BLK;
+    if (kb == 0) load_tile(smem_u32(sm.q[st]), qkv + (int64_t)(s0 + q0) * ld + h * D, ld, L - q0);
+    load_tile(smem_u32(sm.k[st]), qkv + (int64_t)(s0 + k0) * ld + hd + h * D, ld, L - k0);
+    load_tile(smem_u32(sm.v[st]), qkv + (int64_t)(s0 + k0) * ld + 2 * hd + h * D, ld, L - k0);
     if (threadIdx.x < BLK) {
       const int j = k0 + threadIdx.x;
-      sValid[threadIdx.x] = (j < L) && (key_valid == nullptr || key_valid[s0 + j] != 0);
+      sm.valid[st][threadIdx.x] = (j < L) && (key_valid == nullptr || key_valid[s0 + j] != 0);
     }
-    cp_async_wait<0>();
+    cp_async_commit();
+  };
+
+  float o[8][4];
+  float m_i[2], l_i[2];
+  uint32_t qf[4][4];
+  issue(0);
+  for (int it = 0; it < total; ++it) {
+    if (it + 1 < total) {
+      issue(it + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
+    const int hl = it / nkb, kb = it - hl * nkb, st = it & 1, h = h0 + hl, k0 = kb * BLK;
+    const uint32_t uK = smem_u32(sm.k[st]), uV = smem_u32(sm.v[st]);
     if (kb == 0) {
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) lda(qf[kk], uQ, warp * 16, kk, lane);
+      for (int kk = 0; kk < 4; ++kk) lda(qf[kk], smem_u32(sm.q[st]), warp * 16, kk, lane);
+      zero_acc(o);
+      m_i[0] = m_i[1] = -INFINITY;
+      l_i[0] = l_i[1] = 0.f;
     }
+    const int npairs = (min(BLK, L - k0) + 15) >> 4;      // 16-key pairs of this block that hold real keys
+    const bool warp_active = warp * 16 < L - q0;          // warps whose 16 query rows are all padding idle
     float s[8][4];
     zero_acc(s);
+    if (warp_active) {
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
+        if (np >= npairs) break;
         uint32_t bf[4];
         ldb_nk(bf, uK, np * 16, kk, lane);
         mma_bf16_16816(s[2 * np], qf[kk], bf[0], bf[1]);
         mma_bf16_16816(s[2 * np + 1], qf[kk], bf[2], bf[3]);
       }
     }
-    // mask
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
+      if (nt >= 2 * npairs) break;
       const int c = nt * 8 + (lane & 3) * 2;
-      const bool v0 = sValid[c], v1 = sValid[c + 1];
+      const bool v0 = sm.valid[st][c], v1 = sm.valid[st][c + 1];
       if (!v0) s[nt][0] = s[nt][2] = -INFINITY;
       if (!v1) s[nt][1] = s[nt][3] = -INFINITY;
     }
-    // online softmax (rows r=0: lane/4, r=1: lane/4+8)
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
+    for (int r = 0; r < 2; ++r) {     // online softmax (rows r=0: lane/4, r=1: lane/4+8)
       float mx = -INFINITY;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) mx = fmaxf(mx, fmaxf(s[nt][2 * r], s[nt][2 * r + 1]));
+      for (int nt = 0; nt < 8; ++nt)
+        if (nt < 2 * npairs) mx = fmaxf(mx, fmaxf(s[nt][2 * r], s[nt][2 * r + 1]));
       mx = quad_max(mx);
       const float m_new = fmaxf(m_i[r], mx);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = exp2f((m_i[r] - m_use) * sl2);
+      const float corr = ex2_approx((m_i[r] - m_use) * sl2);
       m_i[r] = m_new;
       float rs = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        const float p0 = exp2f((s[nt][2 * r] - m_use) * sl2), p1 = exp2f((s[nt][2 * r + 1] - m_use) * sl2);
-        s[nt][2 * r] = p0;
-        s[nt][2 * r + 1] = p1;
-        rs += p0 + p1;
+        if (nt < 2 * npairs) {
+          const float p0 = ex2_approx((s[nt][2 * r] - m_use) * sl2), p1 = ex2_approx((s[nt][2 * r + 1] - m_use) * sl2);
+          s[nt][2 * r] = p0;
+          s[nt][2 * r + 1] = p1;
+          rs += p0 + p1;
+        }
         o[nt][2 * r] *= corr;
         o[nt][2 * r + 1] *= corr;
       }
@@ -190,27 +224,34 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int tq = s0 + q0 + warp * 16 + (lane >> 2) + ((e >> 1) << 3);
-          const int j = k0 + nt * 8 + (lane & 3) * 2 + (e & 1);
-          s[nt][e] = dropout_keep(seed, pidx(h, T, tq, j), thr) ? s[nt][e] * rscale : 0.f;
+        for (int r = 0; r < 2; ++r) {
+          if (nt >= 2 * npairs) continue;
+          const int tq = s0 + q0 + warp * 16 + (lane >> 2) + 8 * r;
+          const int j = k0 + nt * 8 + (lane & 3) * 2;
+          bool keep0, keep1;
+          dropout_keep2(seed, pidx(h, T, tq, j), thr, keep0, keep1);
+          s[nt][2 * r] = keep0 ? s[nt][2 * r] * rscale : 0.f;
+          s[nt][2 * r + 1] = keep1 ? s[nt][2 * r + 1] * rscale : 0.f;
         }
     }
-    mma_p_b_kn(o, s, uV, lane);
-    __syncthreads();
-  }
+    mma_p_b_kn(o, s, uV, lane, npairs);
+    }   // warp_active
+    if (kb == nkb - 1 && warp_active) {
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const float l = quad_sum(l_i[r]);
-    const int row = q0 + warp * 16 + (lane >> 2) + 8 * r;
-    if (row < L) {
-      const float inv = l > 0.f ? 1.0f / l : 0.f;
-      __nv_bfloat16* orow = out + (int64_t)(s0 + row) * hd + h * D + (lane & 3) * 2;
+      for (int r = 0; r < 2; ++r) {
+        const float l = quad_sum(l_i[r]);
+        const int row = q0 + warp * 16 + (lane >> 2) + 8 * r;
+        if (row < L) {
+          const float inv = l > 0.f ? 1.0f / l : 0.f;
+          __nv_bfloat16* orow = out + (int64_t)(s0 + row) * hd + h * D + (lane & 3) * 2;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-        *reinterpret_cast<uint32_t*>(orow + nt * 8) = pack_bf16x2(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
-      if ((lane & 3) == 0) lse[(int64_t)h * T + s0 + row] = (l > 0.f) ? m_i[r] * scale + logf(l) : 0.f;
+          for (int nt = 0; nt < 8; ++nt)
+            *reinterpret_cast<uint32_t*>(orow + nt * 8) = pack_bf16x2(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
+          if ((lane & 3) == 0) lse[(int64_t)h * T + s0 + row] = (l > 0.f) ? m_i[r] * scale + logf(l) : 0.f;
+        }
+      }
     }
+    __syncthreads();   // this stage is overwritten by the prefetch issued in the next iteration
   }
 }
 
@@ -234,61 +275,87 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
-// One CTA per (key block, head, sequence); warp w owns keys [16w, 16w+16) of the block. Works on S^T = K Q^T so that
-// P^T / dS^T come out of the MMA already in A-fragment layout for the dV = P^T dO and dK = dS^T Q products.
+// One CTA per (key block, head group, sequence); warp w owns keys [16w, 16w+16) of the block. Works on S^T = K Q^T so
+// that P^T / dS^T come out of the MMA already in A-fragment layout for the dV = P^T dO and dK = dS^T Q products.
+// K,V tiles are per head (stage = head parity); Q, dO, lse, delta are per (head, query block) iteration.
+struct DkdvSmem {
+  __nv_bfloat16 k[2][kTile], v[2][kTile], q[2][kTile], dO[2][kTile];
+  float lse[2][BLK], delta[2][BLK];
+};
+
+template <int HPC>
 __global__ void __launch_bounds__(kThreads, 3)
 attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
                      const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
                      const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
                      float scale, uint32_t thr, float rscale, uint32_t seed) {
-  const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int kb = blockIdx.x, h0 = blockIdx.y * HPC, b = blockIdx.z;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   const int k0 = kb * BLK;
   if (k0 >= L) return;
-  __shared__ __align__(128) __nv_bfloat16 sK[BLK * D], sV[BLK * D], sQ[BLK * D], sdO[BLK * D];
-  __shared__ float sLse[BLK], sDelta[BLK];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  DkdvSmem& sm = *reinterpret_cast<DkdvSmem*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t ld = 3 * heads * D;
   const int hd = heads * D;
-  const uint32_t uK = smem_u32(sK), uV = smem_u32(sV), uQ = smem_u32(sQ), uO = smem_u32(sdO);
-  load_tile(uK, qkv + (int64_t)(s0 + k0) * ld + hd + h * D, ld, L - k0);
-  load_tile(uV, qkv + (int64_t)(s0 + k0) * ld + 2 * hd + h * D, ld, L - k0);
-  // validity of this thread's two key rows (S^T rows: lane/4 and lane/4+8 inside the warp's 16 keys)
-  bool kval[2];
+  const int nqb = (L + BLK - 1) / BLK;
+  const int total = HPC * nqb;
+  const float sl2 = scale * kLog2e;
+  bool kval[2];   // validity of this thread's two key rows (S^T rows lane/4 and lane/4+8 of the warp's 16 keys)
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int j = k0 + warp * 16 + (lane >> 2) + 8 * r;
     kval[r] = (j < L) && (key_valid == nullptr || key_valid[s0 + j] != 0);
   }
-  float dk[8][4], dv[8][4];
-  zero_acc(dk);
-  zero_acc(dv);
-  const float sl2 = scale * kLog2e;
-  const int nqb = (L + BLK - 1) / BLK;
-  for (int qb = 0; qb < nqb; ++qb) {
-    const int q0 = qb * BLK;
-    load_tile(uQ, qkv + (int64_t)(s0 + q0) * ld + h * D, ld, L - q0);
-    load_tile(uO, dout + (int64_t)(s0 + q0) * hd + h * D, hd, L - q0);
-    cp_async_commit();
+
+  auto issue = [&](int it) {
+    const int hl = it / nqb, qb = it - hl * nqb, st = it & 1, hs = hl & 1, h = h0 + hl, q0 = qb * BLK;
+    if (qb == 0) {
+      load_tile(smem_u32(sm.k[hs]), qkv + (int64_t)(s0 + k0) * ld + hd + h * D, ld, L - k0);
+      load_tile(smem_u32(sm.v[hs]), qkv + (int64_t)(s0 + k0) * ld + 2 * hd + h * D, ld, L - k0);
+    }
+    load_tile(smem_u32(sm.q[st]), qkv + (int64_t)(s0 + q0) * ld + h * D, ld, L - q0);
+    load_tile(smem_u32(sm.dO[st]), dout + (int64_t)(s0 + q0) * hd + h * D, hd, L - q0);
     if (threadIdx.x < BLK) {
       const int q = q0 + threadIdx.x;
-      sLse[threadIdx.x] = q < L ? lse[(int64_t)h * T + s0 + q] * kLog2e : INFINITY;  // +inf -> P = 0 for padded queries
-      sDelta[threadIdx.x] = q < L ? delta[(int64_t)h * T + s0 + q] : 0.f;
+      sm.lse[st][threadIdx.x] = q < L ? lse[(int64_t)h * T + s0 + q] * kLog2e : INFINITY;   // +inf -> P = 0 (padded query)
+      sm.delta[st][threadIdx.x] = q < L ? delta[(int64_t)h * T + s0 + q] : 0.f;
     }
-    cp_async_wait<0>();
+    cp_async_commit();
+  };
+
+  float dk[8][4], dv[8][4];
+  issue(0);
+  for (int it = 0; it < total; ++it) {
+    if (it + 1 < total) {
+      issue(it + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
-    float st[8][4], dpt[8][4];
-    zero_acc(st);
+    const int hl = it / nqb, qb = it - hl * nqb, st = it & 1, hs = hl & 1, h = h0 + hl, q0 = qb * BLK;
+    const uint32_t uK = smem_u32(sm.k[hs]), uV = smem_u32(sm.v[hs]), uQ = smem_u32(sm.q[st]), uO = smem_u32(sm.dO[st]);
+    if (qb == 0) {
+      zero_acc(dk);
+      zero_acc(dv);
+    }
+    const int npq = (min(BLK, L - q0) + 15) >> 4;         // 16-query pairs of this block that hold real queries
+    const bool warp_active = warp * 16 < L - k0;          // warps whose 16 key rows are all padding idle
+    if (warp_active) {
+    float st_[8][4], dpt[8][4];
+    zero_acc(st_);
     zero_acc(dpt);
-    mma_a_tile_b_nk(st, uK, warp * 16, uQ, lane);    // S^T  [16 keys x 64 queries]
-    mma_a_tile_b_nk(dpt, uV, warp * 16, uO, lane);   // dP^T [16 keys x 64 queries]
+    mma_a_tile_b_nk(st_, uK, warp * 16, uQ, lane, npq);   // S^T  [16 keys x 64 queries]
+    mma_a_tile_b_nk(dpt, uV, warp * 16, uO, lane, npq);   // dP^T [16 keys x 64 queries]
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
+        if (nt >= 2 * npq) continue;
         const int qc = nt * 8 + (lane & 3) * 2 + (e & 1);
         const int r = e >> 1;
-        float p = kval[r] ? exp2f(st[nt][e] * sl2 - sLse[qc]) : 0.f;
+        const float p = kval[r] ? ex2_approx(st_[nt][e] * sl2 - sm.lse[st][qc]) : 0.f;
         float dp = dpt[nt][e];
         float pd = p;
         if (thr) {
@@ -298,80 +365,116 @@ attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __res
           pd = keep ? p * rscale : 0.f;
           dp = keep ? dp * rscale : 0.f;
         }
-        st[nt][e] = pd;                               // dropped P^T  -> dV
-        dpt[nt][e] = p * (dp - sDelta[qc]);           // dS^T         -> dK
+        st_[nt][e] = pd;                                   // dropped P^T  -> dV
+        dpt[nt][e] = p * (dp - sm.delta[st][qc]);          // dS^T         -> dK
       }
-    mma_p_b_kn(dv, st, uO, lane);    // dV += P^T dO   (B = dO [q][d])
-    mma_p_b_kn(dk, dpt, uQ, lane);   // dK += dS^T Q   (B = Q  [q][d])
-    __syncthreads();
-  }
+    mma_p_b_kn(dv, st_, uO, lane, npq);   // dV += P^T dO   (B = dO [q][d])
+    mma_p_b_kn(dk, dpt, uQ, lane, npq);   // dK += dS^T Q   (B = Q  [q][d])
+    }   // warp_active
+    if (qb == nqb - 1 && warp_active) {
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int row = k0 + warp * 16 + (lane >> 2) + 8 * r;
-    if (row < L) {
-      __nv_bfloat16* krow = dqkv + (int64_t)(s0 + row) * ld + hd + h * D + (lane & 3) * 2;
-      __nv_bfloat16* vrow = krow + hd;
+      for (int r = 0; r < 2; ++r) {
+        const int row = k0 + warp * 16 + (lane >> 2) + 8 * r;
+        if (row < L) {
+          __nv_bfloat16* krow = dqkv + (int64_t)(s0 + row) * ld + hd + h * D + (lane & 3) * 2;
+          __nv_bfloat16* vrow = krow + hd;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        *reinterpret_cast<uint32_t*>(krow + nt * 8) = pack_bf16x2(dk[nt][2 * r] * scale, dk[nt][2 * r + 1] * scale);
-        *reinterpret_cast<uint32_t*>(vrow + nt * 8) = pack_bf16x2(dv[nt][2 * r], dv[nt][2 * r + 1]);
+          for (int nt = 0; nt < 8; ++nt) {
+            *reinterpret_cast<uint32_t*>(krow + nt * 8) = pack_bf16x2(dk[nt][2 * r] * scale, dk[nt][2 * r + 1] * scale);
+            *reinterpret_cast<uint32_t*>(vrow + nt * 8) = pack_bf16x2(dv[nt][2 * r], dv[nt][2 * r + 1]);
+          }
+        }
       }
     }
+    __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dQ
-__global__ void __launch_bounds__(kThreads, 4)
+// One CTA per (query block, head group, sequence). Q, dO, lse, delta are per head (stage = head parity); K, V and the
+// key-validity row are per (head, key block) iteration.
+struct DqSmem {
+  __nv_bfloat16 q[2][kTile], dO[2][kTile], k[2][kTile], v[2][kTile];
+  float lse[2][BLK], delta[2][BLK];
+  uint8_t valid[2][BLK];
+};
+
+template <int HPC>
+__global__ void __launch_bounds__(kThreads, 3)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
                    const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
                    float scale, uint32_t thr, float rscale, uint32_t seed) {
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qb = blockIdx.x, h0 = blockIdx.y * HPC, b = blockIdx.z;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   const int q0 = qb * BLK;
   if (q0 >= L) return;
-  __shared__ __align__(128) __nv_bfloat16 sQ[BLK * D], sdO[BLK * D], sK[BLK * D], sV[BLK * D];
-  __shared__ uint8_t sValid[BLK];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  DqSmem& sm = *reinterpret_cast<DqSmem*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t ld = 3 * heads * D;
   const int hd = heads * D;
-  const uint32_t uK = smem_u32(sK), uV = smem_u32(sV), uQ = smem_u32(sQ), uO = smem_u32(sdO);
-  load_tile(uQ, qkv + (int64_t)(s0 + q0) * ld + h * D, ld, L - q0);
-  load_tile(uO, dout + (int64_t)(s0 + q0) * hd + h * D, hd, L - q0);
-  float lse2[2], dl[2];
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int q = q0 + warp * 16 + (lane >> 2) + 8 * r;
-    lse2[r] = q < L ? lse[(int64_t)h * T + s0 + q] * kLog2e : INFINITY;
-    dl[r] = q < L ? delta[(int64_t)h * T + s0 + q] : 0.f;
-  }
-  float dq[8][4];
-  zero_acc(dq);
-  const float sl2 = scale * kLog2e;
   const int nkb = (L + BLK - 1) / BLK;
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int k0 = kb * BLK;
-    load_tile(uK, qkv + (int64_t)(s0 + k0) * ld + hd + h * D, ld, L - k0);
-    load_tile(uV, qkv + (int64_t)(s0 + k0) * ld + 2 * hd + h * D, ld, L - k0);
-    cp_async_commit();
+  const int total = HPC * nkb;
+  const float sl2 = scale * kLog2e;
+
+  auto issue = [&](int it) {
+    const int hl = it / nkb, kb = it - hl * nkb, st = it & 1, hs = hl & 1, h = h0 + hl, k0 = kb * BLK;
+    if (kb == 0) {
+      load_tile(smem_u32(sm.q[hs]), qkv + (int64_t)(s0 + q0) * ld + h * D, ld, L - q0);
+      load_tile(smem_u32(sm.dO[hs]), dout + (int64_t)(s0 + q0) * hd + h * D, hd, L - q0);
+      if (threadIdx.x >= BLK) {
+        const int i = threadIdx.x - BLK, q = q0 + i;
+        sm.lse[hs][i] = q < L ? lse[(int64_t)h * T + s0 + q] * kLog2e : INFINITY;
+        sm.delta[hs][i] = q < L ? delta[(int64_t)h * T + s0 + q] : 0.f;
+      }
+    }
+    load_tile(smem_u32(sm.k[st]), qkv + (int64_t)(s0 + k0) * ld + hd + h * D, ld, L - k0);
+    load_tile(smem_u32(sm.v[st]), qkv + (int64_t)(s0 + k0) * ld + 2 * hd + h * D, ld, L - k0);
     if (threadIdx.x < BLK) {
       const int j = k0 + threadIdx.x;
-      sValid[threadIdx.x] = (j < L) && (key_valid == nullptr || key_valid[s0 + j] != 0);
+      sm.valid[st][threadIdx.x] = (j < L) && (key_valid == nullptr || key_valid[s0 + j] != 0);
     }
-    cp_async_wait<0>();
+    cp_async_commit();
+  };
+
+  float dq[8][4];
+  float lse2[2], dl[2];
+  issue(0);
+  for (int it = 0; it < total; ++it) {
+    if (it + 1 < total) {
+      issue(it + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
+    const int hl = it / nkb, kb = it - hl * nkb, st = it & 1, hs = hl & 1, h = h0 + hl, k0 = kb * BLK;
+    const uint32_t uK = smem_u32(sm.k[st]), uV = smem_u32(sm.v[st]), uQ = smem_u32(sm.q[hs]), uO = smem_u32(sm.dO[hs]);
+    if (kb == 0) {
+      zero_acc(dq);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        lse2[r] = sm.lse[hs][warp * 16 + (lane >> 2) + 8 * r];
+        dl[r] = sm.delta[hs][warp * 16 + (lane >> 2) + 8 * r];
+      }
+    }
+    const int npk = (min(BLK, L - k0) + 15) >> 4;
+    const bool warp_active = warp * 16 < L - q0;
+    if (warp_active) {
     float s[8][4], dp[8][4];
     zero_acc(s);
     zero_acc(dp);
-    mma_a_tile_b_nk(s, uQ, warp * 16, uK, lane);     // S  [16 q x 64 keys]
-    mma_a_tile_b_nk(dp, uO, warp * 16, uV, lane);    // dP [16 q x 64 keys] = dO V^T
+    mma_a_tile_b_nk(s, uQ, warp * 16, uK, lane, npk);     // S  [16 q x 64 keys]
+    mma_a_tile_b_nk(dp, uO, warp * 16, uV, lane, npk);    // dP [16 q x 64 keys] = dO V^T
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
+        if (nt >= 2 * npk) continue;
         const int kc = nt * 8 + (lane & 3) * 2 + (e & 1);
         const int r = e >> 1;
-        const float p = sValid[kc] ? exp2f(s[nt][e] * sl2 - lse2[r]) : 0.f;
+        const float p = sm.valid[st][kc] ? ex2_approx(s[nt][e] * sl2 - lse2[r]) : 0.f;
         float d = dp[nt][e];
         if (thr) {
           const int tq = s0 + q0 + warp * 16 + (lane >> 2) + 8 * r;
@@ -379,24 +482,33 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restr
         }
         s[nt][e] = p * (d - dl[r]);                   // dS
       }
-    mma_p_b_kn(dq, s, uK, lane);                      // dQ += dS K   (B = K [key][d])
-    __syncthreads();
-  }
+    mma_p_b_kn(dq, s, uK, lane, npk);                 // dQ += dS K   (B = K [key][d])
+    }   // warp_active
+    if (kb == nkb - 1 && warp_active) {
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int row = q0 + warp * 16 + (lane >> 2) + 8 * r;
-    if (row < L) {
-      __nv_bfloat16* qrow = dqkv + (int64_t)(s0 + row) * ld + h * D + (lane & 3) * 2;
+      for (int r = 0; r < 2; ++r) {
+        const int row = q0 + warp * 16 + (lane >> 2) + 8 * r;
+        if (row < L) {
+          __nv_bfloat16* qrow = dqkv + (int64_t)(s0 + row) * ld + h * D + (lane & 3) * 2;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-        *reinterpret_cast<uint32_t*>(qrow + nt * 8) = pack_bf16x2(dq[nt][2 * r] * scale, dq[nt][2 * r + 1] * scale);
+          for (int nt = 0; nt < 8; ++nt)
+            *reinterpret_cast<uint32_t*>(qrow + nt * 8) = pack_bf16x2(dq[nt][2 * r] * scale, dq[nt][2 * r + 1] * scale);
+        }
+      }
     }
+    __syncthreads();
   }
 }
 
 inline uint32_t drop_threshold(float p) {
   const double t = (double)p * 65536.0 + 0.5;   // 16-bit threshold (ptx.cuh dropout_keep)
   return p <= 0.f ? 0u : (t >= 65535.0 ? 65535u : (uint32_t)t);
+}
+
+template <typename K>
+int set_smem(nbest_ctx* ctx, K kernel, size_t bytes) {
+  NBEST_CHECK_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return NBEST_OK;
 }
 
 }  // namespace
@@ -409,10 +521,26 @@ extern "C" int nbest_attn_varlen_fwd(nbest_ctx* ctx, const void* qkv_bf16, const
   NBEST_CHECK_ARG(ctx, B > 0 && heads > 0 && max_len > 0 && max_len <= 512, "need 0 < max_len <= 512 (BERT position limit)");
   NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
   NBEST_CHECK_ARG(ctx, B <= 65535, "B too large for one launch");
-  const dim3 grid((max_len + BLK - 1) / BLK, heads, B);
-  attn_fwd_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), cu_seqlens, key_valid, heads, T,
-      reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, 0.125f, drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed);
+  const auto* q = reinterpret_cast<const __nv_bfloat16*>(qkv_bf16);
+  auto* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const uint32_t thr = drop_threshold(p_drop);
+  const float rscale = 1.0f / (1.0f - p_drop);
+  const int nqb = (max_len + BLK - 1) / BLK;
+  static bool attr = false;
+  if (!attr) {
+    int rc = set_smem(ctx, attn_fwd_kernel<4>, sizeof(FwdSmem));
+    if (rc) return rc;
+    rc = set_smem(ctx, attn_fwd_kernel<1>, sizeof(FwdSmem));
+    if (rc) return rc;
+    attr = true;
+  }
+  if (heads % 4 == 0)
+    attn_fwd_kernel<4><<<dim3(nqb, heads / 4, B), kThreads, sizeof(FwdSmem), s>>>(q, cu_seqlens, key_valid, heads, T, o, lse,
+                                                                              0.125f, thr, rscale, seed);
+  else
+    attn_fwd_kernel<1><<<dim3(nqb, heads, B), kThreads, sizeof(FwdSmem), s>>>(q, cu_seqlens, key_valid, heads, T, o, lse, 0.125f,
+                                                                          thr, rscale, seed);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
@@ -420,29 +548,50 @@ extern "C" int nbest_attn_varlen_fwd(nbest_ctx* ctx, const void* qkv_bf16, const
 extern "C" int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens,
                                      const uint8_t* key_valid, int B, int max_len, int heads, int T, int T_active,
                                      const void* out_bf16, const void* dout_bf16, const float* lse, void* dqkv_bf16,
-                                     float* delta_ws, float p_drop,
-                                     uint32_t seed, void* stream) {
+                                     float* delta_ws, float p_drop, uint32_t seed, void* stream) {
   if (!ctx) return NBEST_EINVAL;
   NBEST_CHECK_ARG(ctx, qkv_bf16 && cu_seqlens && out_bf16 && dout_bf16 && lse && dqkv_bf16 && delta_ws, "null pointer");
   NBEST_CHECK_ARG(ctx, B > 0 && heads > 0 && max_len > 0 && max_len <= 512, "need 0 < max_len <= 512 (BERT position limit)");
   NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
   NBEST_CHECK_ARG(ctx, B <= 65535, "B too large for one launch");
+  NBEST_CHECK_ARG(ctx, T_active >= 0 && T_active <= T, "need 0 <= T_active <= T");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const auto* q = reinterpret_cast<const __nv_bfloat16*>(qkv_bf16);
   const auto* o = reinterpret_cast<const __nv_bfloat16*>(out_bf16);
   const auto* g = reinterpret_cast<const __nv_bfloat16*>(dout_bf16);
   auto* dq = reinterpret_cast<__nv_bfloat16*>(dqkv_bf16);
-  NBEST_CHECK_ARG(ctx, T_active >= 0 && T_active <= T, "need 0 <= T_active <= T");
   if (T_active > 0) {
     attn_delta_kernel<<<(T_active + 7) / 8, 256, 0, s>>>(o, g, T_active, T, heads, delta_ws);
     NBEST_CHECK_LAUNCH(ctx);
   }
-  const dim3 grid((max_len + BLK - 1) / BLK, heads, B);
+  static bool attr = false;
+  if (!attr) {
+    int rc = set_smem(ctx, attn_bwd_dkdv_kernel<4>, sizeof(DkdvSmem));
+    if (!rc) rc = set_smem(ctx, attn_bwd_dkdv_kernel<1>, sizeof(DkdvSmem));
+    if (!rc) rc = set_smem(ctx, attn_bwd_dq_kernel<4>, sizeof(DqSmem));
+    if (!rc) rc = set_smem(ctx, attn_bwd_dq_kernel<1>, sizeof(DqSmem));
+    if (rc) return rc;
+    attr = true;
+  }
+  const int nb = (max_len + BLK - 1) / BLK;
   const uint32_t thr = drop_threshold(p_drop);
   const float rscale = 1.0f / (1.0f - p_drop);
-  attn_bwd_dkdv_kernel<<<grid, kThreads, 0, s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f, thr, rscale, seed);
-  NBEST_CHECK_LAUNCH(ctx);
-  attn_bwd_dq_kernel<<<grid, kThreads, 0, s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f, thr, rscale, seed);
-  NBEST_CHECK_LAUNCH(ctx);
+  if (heads % 4 == 0) {
+    const dim3 grid(nb, heads / 4, B);
+    attn_bwd_dkdv_kernel<4><<<grid, kThreads, sizeof(DkdvSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq,
+                                                                    0.125f, thr, rscale, seed);
+    NBEST_CHECK_LAUNCH(ctx);
+    attn_bwd_dq_kernel<4><<<grid, kThreads, sizeof(DqSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f,
+                                                                thr, rscale, seed);
+    NBEST_CHECK_LAUNCH(ctx);
+  } else {
+    const dim3 grid(nb, heads, B);
+    attn_bwd_dkdv_kernel<1><<<grid, kThreads, sizeof(DkdvSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq,
+                                                                    0.125f, thr, rscale, seed);
+    NBEST_CHECK_LAUNCH(ctx);
+    attn_bwd_dq_kernel<1><<<grid, kThreads, sizeof(DqSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f,
+                                                                thr, rscale, seed);
+    NBEST_CHECK_LAUNCH(ctx);
+  }
   return NBEST_OK;
 }

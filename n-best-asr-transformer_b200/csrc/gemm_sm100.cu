@@ -13,6 +13,8 @@
 // Operand majorness is a template flag: K-major operands are read as {64 x rows} TMA boxes (one per stage), MN-major
 // operands (dgrad weights, both wgrad operands) as 64-column x 64-k-row boxes laid out as the canonical MN-major
 // SWIZZLE_128B UMMA layout (LBO = 8 KiB between 64-element chunks, SBO = 1 KiB between 8-row groups).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -23,7 +25,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kEpiWarp0 = 2;
-constexpr int kEpiWarps = 8;   // two per TMEM lane quarter: they split the tile's 32-column chunks (even / odd)
+constexpr int kEpiWarps = 16;  // four per TMEM lane quarter: they interleave the tile's 32-column chunks
+constexpr int kChunkStride = kEpiWarps / 4;
 constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
 constexpr uint32_t kChunkBytes = 64 * BK * 2;  // one 64-row (or 64-col) x 64 bf16 box = 8 KiB
 
@@ -176,7 +179,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------------------------------------------ epilogue (4 warps, one TMEM lane quarter each)
     const int q = warp & 3;  // tcgen05.ld: warp w may only touch lanes [32*(w%4), 32*(w%4)+32)
     uint8_t* st = staging + (warp - kEpiWarp0) * 2048;
-    const int c_first = (warp - kEpiWarp0) >> 2;  // this warp handles chunks c_first, c_first + 2, ...
+    const int c_first = (warp - kEpiWarp0) >> 2;  // this warp handles chunks c_first, c_first + kChunkStride, ...
     const uint32_t st_u32 = smem_u32(st);
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
@@ -201,7 +204,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = c_first; c < BN / 32; c += 2) {
+      for (int c = c_first; c < BN / 32; c += kChunkStride) {
         const int nc = n0 + c * 32;
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + c * 32, r);
@@ -210,13 +213,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<uint4*>(st + stage_off(i * 8 + crow, cseg)) = aux_next[i];
-          if (c + 2 < BN / 32) {
+          if (c + kChunkStride < BN / 32) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int gr = m0 + q * 32 + i * 8 + crow;
               aux_next[i] = make_uint4(0, 0, 0, 0);
               if (gr < g.M)
-                aux_next[i] = __ldg(reinterpret_cast<const uint4*>(g.aux + (int64_t)gr * g.ldaux + nc + 64 + cseg * 8));
+                aux_next[i] = __ldg(reinterpret_cast<const uint4*>(g.aux + (int64_t)gr * g.ldaux + nc + 32 * kChunkStride + cseg * 8));
             }
           }
           __syncwarp();
@@ -396,7 +399,16 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
   NBEST_CHECK_ARG(ctx, !needs_aux || (aux_bf16 && ldaux % 8 == 0), "epilogue needs aux with ldaux % 8 == 0");
   NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
 
-  const int BN = (N % 256 == 0) ? 256 : 128;
+  // 128 x 256 tiles halve the smem operand traffic per MMA; short-K problems with few tiles (out-proj: N = K = 768)
+  // prefer 128 x 128 so that the persistent CTAs see more, shorter tiles (less fill / drain / wave quantisation).
+  int BN = (N % 256 == 0) ? 256 : 128;
+  if (BN == 256 && epilogue != NBEST_EPI_ACCUM_F32 && K <= 1024 &&
+      (int64_t)((M + BM - 1) / BM) * (N / 256) < 4LL * ctx->num_sms)
+    BN = 128;
+  if (const char* force = getenv("NBEST_GEMM_BN")) {
+    const int f = atoi(force);
+    if ((f == 128 || f == 256) && N % f == 0) BN = f;
+  }
   GemmArgs g;
   g.M = M;
   g.N = N;

@@ -181,27 +181,37 @@ __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t idx, uint32
 
 // erf-based GELU pieces. Phi(z) = 0.5*(1+erf(z/sqrt2)) via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7 + approx-rcp/ex2
 // error ~1e-6), phi(z) = exp(-z^2/2)/sqrt(2*pi). Far below bf16 resolution of the result; ~16 instructions, 2 MUFU.
-__device__ __forceinline__ void gelu_parts(float z, float& Phi, float& phi) {
-  const float x = fabsf(z) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
-  const float e = exp2f(x * x * -1.4426950408889634f);
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// h = 0.5*(1 - erf(|z|/sqrt2)) and e = exp(-z^2/2), with xs = |z|*sqrt(log2(e)/2) so that e = 2^(-xs^2).
+__device__ __forceinline__ void gelu_tail(float z, float& h, float& e) {
+  const float xs = fabsf(z) * 0.8493218002880191f;
+  const float t = rcp_approx(fmaf(0.2727374808792225f, xs, 1.0f));   // 1 / (1 + 0.3275911 |z|/sqrt2)
+  e = ex2_approx(-xs * xs);
   float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
   poly = fmaf(poly, t, 0.5f * 1.421413741f);
   poly = fmaf(poly, t, 0.5f * -0.284496736f);
   poly = fmaf(poly, t, 0.5f * 0.254829592f);
-  const float half_tail = poly * t * e;  // 0.5*(1-erf(x))
-  Phi = z >= 0.f ? 1.0f - half_tail : half_tail;
-  phi = 0.39894228040143268f * e;
+  h = poly * t * e;
 }
-__device__ __forceinline__ float gelu_fwd(float z) {
-  float P, p;
-  gelu_parts(z, P, p);
-  return z * P;
+__device__ __forceinline__ float gelu_fwd(float z) {   // z*Phi(z) = 0.5 z + |z| (0.5 - h)
+  float h, e;
+  gelu_tail(z, h, e);
+  return fmaf(fabsf(z), 0.5f - h, 0.5f * z);
 }
-__device__ __forceinline__ float gelu_grad(float z) {
-  float P, p;
-  gelu_parts(z, P, p);
-  return fmaf(z, p, P);
+__device__ __forceinline__ float gelu_grad(float z) {  // Phi(z) + z phi(z)
+  float h, e;
+  gelu_tail(z, h, e);
+  const float Phi = 0.5f + copysignf(0.5f - h, z);
+  return fmaf(z * 0.39894228040143268f, e, Phi);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
