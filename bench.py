@@ -164,8 +164,11 @@ def main():
     from nbest_b200.synth import synth_batch
     from nbest_b200.trainer import DataParallelTrainer, init_distributed
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NBEST_KEEP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL banners go to stdout; stdout carries exactly one JSON line
+    # NCCL prints its version banner to stdout from C; stdout must carry exactly one JSON line, so everything up to
+    # the final print goes to stderr.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU port)")
     rank, local, world = init_distributed()
@@ -229,6 +232,9 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), ctx.launches() - l0, out
 
+    if world > 1:
+        for i in range(5):          # communicator bring-up (NVLS buffers, channel setup) before the W warm-up steps
+            step_dev(i)
     for i in range(args.warmup):
         step_dev(i)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -297,7 +303,9 @@ def main():
             line["cpu_baseline"] = dict(value=n_utt / med, unit=UNIT, cores=threads, kind="port",
                                         sample="%d-utterance batch (BASELINE configs[0] shape), 1 warm-up + 2 timed steps, %.1f s" % (
                                             n_utt, total), ms_per_step=med * 1e3)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

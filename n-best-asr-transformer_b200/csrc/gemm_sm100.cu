@@ -5,8 +5,9 @@
 // BertIntermediate.dense + GELU (:339-342), BertOutput.dense (:352-356), and their autograd products
 // (dgrad / wgrad of n_best_asr_bert.py:264 `total_loss.backward()`).
 //
-// One CTA per SM (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
-// warps 2..9 = epilogue (two warps per TMEM lane quarter, splitting the tile's column chunks). Tiles are 128 x BN (BN = 256 or 128) x 64, the smem ring has
+// One CTA per SM (320 threads): warps 0..7 = epilogue (two warps per TMEM lane quarter, each owning 64-column units
+// that leave through TMA stores), warp 8 = TMA producer, warp 9 = TMEM owner + single-thread tcgen05.mma issuer (the issuers have
+// the highest warp ids so the scheduler never parks them behind busy epilogue warps). Tiles are 128 x BN (BN = 256 or 128) x 64, the smem ring has
 // 4 (BN=256) or 6 (BN=128) stages of 128-byte-swizzled operand tiles, and the fp32 accumulator is double buffered
 // in TMEM (2*BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
@@ -24,15 +25,19 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kEpiWarp0 = 2;
-constexpr int kEpiWarps = 16;  // four per TMEM lane quarter: they interleave the tile's 32-column chunks
-constexpr int kChunkStride = kEpiWarps / 4;
-constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
+constexpr int kEpiWarp0 = 0;   // epilogue warps come FIRST: the warp scheduler favours higher warp ids, and the two
+                               // single-thread issuers (TMA, MMA) must never starve behind busy epilogue warps
+constexpr int kEpiWarps = 8;   // two per TMEM lane quarter; each owns whole 64-column units of the tile
+constexpr int kProducerWarp = kEpiWarps;
+constexpr int kMmaWarp = kEpiWarps + 1;
+constexpr int kThreads = 32 * (kEpiWarps + 2);
 constexpr uint32_t kChunkBytes = 64 * BK * 2;  // one 64-row (or 64-col) x 64 bf16 box = 8 KiB
 
 struct GemmArgs {
   int M, N, K;
   int num_m_tiles, num_n_tiles, num_splits, kb_per_split, num_kb;
+  int debug;    // NBEST_GEMM_DEBUG: 1 = epilogue does nothing but release the accumulator, 2 = no global stores
+  int stages;   // smem ring depth in use (<= Cfg::kStages; NBEST_GEMM_STAGES experiments)
   void* C;
   int64_t ldc;
   const float* bias;
@@ -50,13 +55,11 @@ struct Cfg {
   static constexpr uint32_t kABytes = BM * BK * 2;
   static constexpr uint32_t kBBytes = BN * BK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kStagingBytes = kEpiWarps * 2048;  // per epilogue warp: 32 rows x 64 B
+  static constexpr uint32_t kStagingBytes = kEpiWarps * 4096;  // per epilogue warp: one 32-row x 128-byte store unit
   static constexpr uint32_t kBarOffset = kStages * kStageBytes + kStagingBytes;
   static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;  // + barriers + alignment slack
   static constexpr uint32_t kTmemCols = 2 * BN;
 };
-
-__device__ __forceinline__ uint32_t stage_off(int row, int seg) { return row * 64 + ((seg ^ ((row >> 1) & 3)) << 4); }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -64,7 +67,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmArgs g) {
   using C_ = Cfg<BN>;
   constexpr int kStages = C_::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -80,9 +84,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int lane = threadIdx.x & 31;
   const int num_work = g.num_m_tiles * g.num_n_tiles * g.num_splits;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (EPI != NBEST_EPI_ACCUM_F32) tma_prefetch_desc(&tmC);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -93,7 +98,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, C_::kTmemCols);
     tmem_relinquish();
   }
@@ -102,7 +107,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer
     uint32_t stage = 0, phase = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -133,13 +138,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         __syncwarp();
-        if (++stage == kStages) {
+        if (++stage == (uint32_t)g.stages) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     constexpr uint32_t a_lbo = A_MN ? kChunkBytes : 16, b_lbo = B_MN ? kChunkBytes : 16;
@@ -169,18 +174,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         }
         __syncwarp();
-        if (++stage == kStages) {
+        if (++stage == (uint32_t)g.stages) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps, one TMEM lane quarter each)
-    const int q = warp & 3;  // tcgen05.ld: warp w may only touch lanes [32*(w%4), 32*(w%4)+32)
-    uint8_t* st = staging + (warp - kEpiWarp0) * 2048;
-    const int c_first = (warp - kEpiWarp0) >> 2;  // this warp handles chunks c_first, c_first + kChunkStride, ...
-    const uint32_t st_u32 = smem_u32(st);
+    // ------------------------------------------------------------------ epilogue
+    // 8 warps: warp w reads TMEM lane quarter q = w % 4 (tcgen05.ld restriction) and owns the 64-column units
+    // u = w/4, w/4 + 2, ... of the tile. A unit (32 rows x 64 bf16 = 128-byte rows) is assembled in a 4 KiB smem buffer
+    // in the TMA SWIZZLE_128B layout and written with ONE cp.async.bulk.tensor store: full 128-byte lines, the M edge
+    // is clipped by the tensor map. (Per-lane 16-byte st.global of 64-byte row segments cost 17 % of the GEMM.)
+    const int q = warp & 3;
+    const int u_first = warp >> 2;
+    uint8_t* st = staging + warp * 4096;
+    auto unit_off = [](int row, int chunk16) { return row * 128 + ((chunk16 ^ (row & 7)) << 4); };
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
       const int tile = w % (g.num_m_tiles * g.num_n_tiles);
@@ -189,138 +198,128 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int row = m0 + q * 32 + lane;  // the accumulator row this thread owns
       constexpr bool kHasAux = (EPI == NBEST_EPI_BIAS_DROP_RES || EPI == NBEST_EPI_DGELU || EPI == NBEST_EPI_ADD);
-      // coalesced access pattern for aux loads / C stores: 8 rows x 64 B per warp instruction
-      const int crow = lane >> 2, cseg = lane & 3;
+      const int crow = lane >> 2, cseg = lane & 3;   // coalesced aux loads: 8 rows x 64 B per warp instruction
       uint4 aux_next[4];
-      if constexpr (kHasAux) {
+      auto load_aux = [&](int c) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int gr = m0 + q * 32 + i * 8 + crow;
           aux_next[i] = make_uint4(0, 0, 0, 0);
-          if (gr < g.M)
-            aux_next[i] = __ldg(reinterpret_cast<const uint4*>(g.aux + (int64_t)gr * g.ldaux + n0 + c_first * 32 + cseg * 8));
+          if (gr < g.M) aux_next[i] = __ldg(reinterpret_cast<const uint4*>(g.aux + (int64_t)gr * g.ldaux + n0 + c * 32 + cseg * 8));
         }
-      }
+      };
+      if constexpr (kHasAux) load_aux(2 * u_first);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if constexpr (EPI == NBEST_EPI_ACCUM_F32) {
 #pragma unroll 1
-      for (int c = c_first; c < BN / 32; c += kChunkStride) {
-        const int nc = n0 + c * 32;
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + c * 32, r);
-        uint32_t auxrow[16];
-        if constexpr (kHasAux) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(st + stage_off(i * 8 + crow, cseg)) = aux_next[i];
-          if (c + kChunkStride < BN / 32) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int gr = m0 + q * 32 + i * 8 + crow;
-              aux_next[i] = make_uint4(0, 0, 0, 0);
-              if (gr < g.M)
-                aux_next[i] = __ldg(reinterpret_cast<const uint4*>(g.aux + (int64_t)gr * g.ldaux + nc + 32 * kChunkStride + cseg * 8));
-            }
-          }
-          __syncwarp();
-#pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            const uint4 v = *reinterpret_cast<const uint4*>(st + stage_off(lane, s));
-            auxrow[s * 4 + 0] = v.x;
-            auxrow[s * 4 + 1] = v.y;
-            auxrow[s * 4 + 2] = v.z;
-            auxrow[s * 4 + 3] = v.w;
-          }
-          __syncwarp();
-        }
-        tmem_ld_wait();
-
-        if constexpr (EPI == NBEST_EPI_ACCUM_F32) {
-          float* crow_ptr = reinterpret_cast<float*>(g.C) + (int64_t)row * g.ldc + nc;
+        for (int c = u_first; c < BN / 32; c += 2) {
+          if (g.debug == 1) break;
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + c * 32, r);
+          tmem_ld_wait();
+          float* crow_ptr = reinterpret_cast<float*>(g.C) + (int64_t)row * g.ldc + n0 + c * 32;
           if (row < g.M) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               red_add_v4(crow_ptr + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                          __uint_as_float(r[j + 3]));
           }
-        } else {
-          float v[32];
+        }
+      } else {
+#pragma unroll 1
+        for (int u = u_first; u < BN / 64; u += 2) {
+          if (g.debug == 1) break;
+          constexpr int kPasses = (EPI == NBEST_EPI_BIAS_GELU) ? 2 : 1;   // GELU: pass 0 stores u = acc + bias, pass 1 gelu(u)
+#pragma unroll 1
+          for (int pass = 0; pass < kPasses; ++pass) {
+            if (EPI == NBEST_EPI_BIAS_GELU && pass == 0 && g.out2 == nullptr) continue;
+            if (lane == 0) bulk_wait_read();   // the previous store from this buffer has finished reading it
+            __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if constexpr (EPI == NBEST_EPI_BIAS || EPI == NBEST_EPI_BIAS_GELU || EPI == NBEST_EPI_BIAS_DROP_RES) {
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c = 2 * u + cc;
+              const int nc = n0 + c * 32;
+              uint32_t r[32];
+              tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + c * 32, r);
+              uint32_t auxrow[16];
+              if constexpr (kHasAux) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + nc + j));
-              v[j] += b.x;
-              v[j + 1] += b.y;
-              v[j + 2] += b.z;
-              v[j + 3] += b.w;
-            }
-          }
-          uint32_t packed[16];
-          if constexpr (EPI == NBEST_EPI_BIAS_GELU) {
-            if (g.out2 != nullptr) {
+                for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(st + unit_off(i * 8 + crow, cc * 4 + cseg)) = aux_next[i];
+                const int cn = (cc == 0) ? c + 1 : c + 3;   // the next chunk this warp will process
+                if (cn < BN / 32) load_aux(cn);
+                __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-              for (int s = 0; s < 4; ++s)
-                *reinterpret_cast<uint4*>(st + stage_off(lane, s)) =
-                    make_uint4(packed[s * 4], packed[s * 4 + 1], packed[s * 4 + 2], packed[s * 4 + 3]);
-              __syncwarp();
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int gr = m0 + q * 32 + i * 8 + crow;
-                const uint4 o = *reinterpret_cast<const uint4*>(st + stage_off(i * 8 + crow, cseg));
-                if (gr < g.M) *reinterpret_cast<uint4*>(g.out2 + (int64_t)gr * g.ldc + nc + cseg * 8) = o;
+                for (int s4 = 0; s4 < 4; ++s4) {
+                  const uint4 t4 = *reinterpret_cast<const uint4*>(st + unit_off(lane, cc * 4 + s4));
+                  auxrow[s4 * 4 + 0] = t4.x;
+                  auxrow[s4 * 4 + 1] = t4.y;
+                  auxrow[s4 * 4 + 2] = t4.z;
+                  auxrow[s4 * 4 + 3] = t4.w;
+                }
+                __syncwarp();
               }
-              __syncwarp();
-            }
+              tmem_ld_wait();
+              float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_fwd(v[j]);
-          } else if constexpr (EPI == NBEST_EPI_BIAS_DROP_RES) {
-            if (g.drop_thresh != 0) {
-              const uint32_t base = (uint32_t)row * (uint32_t)g.N + (uint32_t)nc;
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+              if constexpr (EPI == NBEST_EPI_BIAS || EPI == NBEST_EPI_BIAS_GELU || EPI == NBEST_EPI_BIAS_DROP_RES) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                bool k0, k1;
-                dropout_keep2(g.seed, base + j, g.drop_thresh, k0, k1);   // base is even (N and nc are even)
-                v[j] = k0 ? v[j] * g.drop_scale : 0.f;
-                v[j + 1] = k1 ? v[j + 1] * g.drop_scale : 0.f;
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + nc + j));
+                  v[j] += b.x;
+                  v[j + 1] += b.y;
+                  v[j + 2] += b.z;
+                  v[j + 3] += b.w;
+                }
               }
-            }
+              if constexpr (EPI == NBEST_EPI_BIAS_GELU) {
+                if (pass == 1) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              v[2 * j] += bf16lo(auxrow[j]);
-              v[2 * j + 1] += bf16hi(auxrow[j]);
-            }
-          } else if constexpr (EPI == NBEST_EPI_DGELU) {
+                  for (int j = 0; j < 32; ++j) v[j] = gelu_fwd(v[j]);
+                }
+              } else if constexpr (EPI == NBEST_EPI_BIAS_DROP_RES) {
+                if (g.drop_thresh != 0) {
+                  const uint32_t base = (uint32_t)row * (uint32_t)g.N + (uint32_t)nc;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              v[2 * j] *= gelu_grad(bf16lo(auxrow[j]));
-              v[2 * j + 1] *= gelu_grad(bf16hi(auxrow[j]));
-            }
-          } else if constexpr (EPI == NBEST_EPI_ADD) {
+                  for (int j = 0; j < 32; j += 2) {
+                    bool k0, k1;
+                    dropout_keep2(g.seed, base + j, g.drop_thresh, k0, k1);   // base is even (N and nc are even)
+                    v[j] = k0 ? v[j] * g.drop_scale : 0.f;
+                    v[j + 1] = k1 ? v[j + 1] * g.drop_scale : 0.f;
+                  }
+                }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              v[2 * j] += bf16lo(auxrow[j]);
-              v[2 * j + 1] += bf16hi(auxrow[j]);
+                for (int j = 0; j < 16; ++j) {
+                  v[2 * j] += bf16lo(auxrow[j]);
+                  v[2 * j + 1] += bf16hi(auxrow[j]);
+                }
+              } else if constexpr (EPI == NBEST_EPI_DGELU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  v[2 * j] *= gelu_grad(bf16lo(auxrow[j]));
+                  v[2 * j + 1] *= gelu_grad(bf16hi(auxrow[j]));
+                }
+              } else if constexpr (EPI == NBEST_EPI_ADD) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  v[2 * j] += bf16lo(auxrow[j]);
+                  v[2 * j + 1] += bf16hi(auxrow[j]);
+                }
+              }
+#pragma unroll
+              for (int s4 = 0; s4 < 4; ++s4)
+                *reinterpret_cast<uint4*>(st + unit_off(lane, cc * 4 + s4)) =
+                    make_uint4(pack_bf16x2(v[8 * s4], v[8 * s4 + 1]), pack_bf16x2(v[8 * s4 + 2], v[8 * s4 + 3]),
+                               pack_bf16x2(v[8 * s4 + 4], v[8 * s4 + 5]), pack_bf16x2(v[8 * s4 + 6], v[8 * s4 + 7]));
+            }
+            fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if (lane == 0 && g.debug != 2) {
+              tma_store_2d((EPI == NBEST_EPI_BIAS_GELU && pass == 0) ? &tmC2 : &tmC, st, n0 + u * 64, m0 + q * 32);
+              bulk_commit();
             }
           }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-          for (int s = 0; s < 4; ++s)
-            *reinterpret_cast<uint4*>(st + stage_off(lane, s)) =
-                make_uint4(packed[s * 4], packed[s * 4 + 1], packed[s * 4 + 2], packed[s * 4 + 3]);
-          __syncwarp();
-          __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(g.C);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int gr = m0 + q * 32 + i * 8 + crow;
-            const uint4 o = *reinterpret_cast<const uint4*>(st + stage_off(i * 8 + crow, cseg));
-            if (gr < g.M) *reinterpret_cast<uint4*>(Cb + (int64_t)gr * g.ldc + nc + cseg * 8) = o;
-          }
-          __syncwarp();
         }
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
@@ -328,18 +327,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (lane == 0) bulk_wait_all();   // every bulk store of this warp is globally complete before the CTA exits
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C_::kTmemCols);
   }
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
-int launch(nbest_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
+int launch(nbest_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
+           const GemmArgs& g, cudaStream_t stream) {
   auto kfn = gemm_kernel<BN, A_MN, B_MN, EPI>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
@@ -348,31 +349,31 @@ int launch(nbest_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const
   }
   const int num_work = g.num_m_tiles * g.num_n_tiles * g.num_splits;
   const int grid = num_work < ctx->num_sms ? num_work : ctx->num_sms;
-  kfn<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(tmA, tmB, g);
+  kfn<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, g);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
 
 template <int BN>
-int dispatch(nbest_ctx* ctx, int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g,
-             cudaStream_t s) {
+int dispatch(nbest_ctx* ctx, int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
+             const CUtensorMap& tmC, const CUtensorMap& tmC2, const GemmArgs& g, cudaStream_t s) {
   if (!a_mn && !b_mn) {
     switch (epi) {
-      case NBEST_EPI_NONE: return launch<BN, false, false, NBEST_EPI_NONE>(ctx, tmA, tmB, g, s);
-      case NBEST_EPI_BIAS: return launch<BN, false, false, NBEST_EPI_BIAS>(ctx, tmA, tmB, g, s);
-      case NBEST_EPI_BIAS_GELU: return launch<BN, false, false, NBEST_EPI_BIAS_GELU>(ctx, tmA, tmB, g, s);
-      case NBEST_EPI_BIAS_DROP_RES: return launch<BN, false, false, NBEST_EPI_BIAS_DROP_RES>(ctx, tmA, tmB, g, s);
+      case NBEST_EPI_NONE: return launch<BN, false, false, NBEST_EPI_NONE>(ctx, tmA, tmB, tmC, tmC2, g, s);
+      case NBEST_EPI_BIAS: return launch<BN, false, false, NBEST_EPI_BIAS>(ctx, tmA, tmB, tmC, tmC2, g, s);
+      case NBEST_EPI_BIAS_GELU: return launch<BN, false, false, NBEST_EPI_BIAS_GELU>(ctx, tmA, tmB, tmC, tmC2, g, s);
+      case NBEST_EPI_BIAS_DROP_RES: return launch<BN, false, false, NBEST_EPI_BIAS_DROP_RES>(ctx, tmA, tmB, tmC, tmC2, g, s);
       default: break;
     }
   } else if (!a_mn && b_mn) {
     switch (epi) {
-      case NBEST_EPI_NONE: return launch<BN, false, true, NBEST_EPI_NONE>(ctx, tmA, tmB, g, s);
-      case NBEST_EPI_DGELU: return launch<BN, false, true, NBEST_EPI_DGELU>(ctx, tmA, tmB, g, s);
-      case NBEST_EPI_ADD: return launch<BN, false, true, NBEST_EPI_ADD>(ctx, tmA, tmB, g, s);
+      case NBEST_EPI_NONE: return launch<BN, false, true, NBEST_EPI_NONE>(ctx, tmA, tmB, tmC, tmC2, g, s);
+      case NBEST_EPI_DGELU: return launch<BN, false, true, NBEST_EPI_DGELU>(ctx, tmA, tmB, tmC, tmC2, g, s);
+      case NBEST_EPI_ADD: return launch<BN, false, true, NBEST_EPI_ADD>(ctx, tmA, tmB, tmC, tmC2, g, s);
       default: break;
     }
   } else if (a_mn && b_mn) {
-    if (epi == NBEST_EPI_ACCUM_F32) return launch<BN, true, true, NBEST_EPI_ACCUM_F32>(ctx, tmA, tmB, g, s);
+    if (epi == NBEST_EPI_ACCUM_F32) return launch<BN, true, true, NBEST_EPI_ACCUM_F32>(ctx, tmA, tmB, tmC, tmC2, g, s);
   }
   nbest_set_error(ctx, "nbest_gemm_bf16: unsupported (a_mn_major=%d, b_mn_major=%d, epilogue=%d) combination", a_mn, b_mn,
                   epi);
@@ -426,6 +427,12 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
     if (want < 1) want = 1;
     g.num_splits = want;
   }
+  g.debug = getenv("NBEST_GEMM_DEBUG") ? atoi(getenv("NBEST_GEMM_DEBUG")) : 0;
+  g.stages = (BN == 256) ? Cfg<256>::kStages : Cfg<128>::kStages;
+  if (const char* st = getenv("NBEST_GEMM_STAGES")) {
+    const int v = atoi(st);
+    if (v >= 1 && v < g.stages) g.stages = v;
+  }
   g.kb_per_split = (g.num_kb + g.num_splits - 1) / g.num_splits;
   g.num_splits = (g.num_kb + g.kb_per_split - 1) / g.kb_per_split;  // no empty split
   g.C = C;
@@ -457,7 +464,17 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
     rc = nbest_make_tmap_bf16(ctx, &tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64);
   if (rc != NBEST_OK) return rc;
 
+  // output tensor maps for the epilogue's TMA stores: {64 columns x 32 rows} boxes of the bf16 result(s)
+  CUtensorMap tmC = tmA, tmC2 = tmA;
+  if (epilogue != NBEST_EPI_ACCUM_F32) {
+    rc = nbest_make_tmap_bf16(ctx, &tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32);
+    if (rc != NBEST_OK) return rc;
+    if (epilogue == NBEST_EPI_BIAS_GELU && out2_bf16) {
+      rc = nbest_make_tmap_bf16(ctx, &tmC2, out2_bf16, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32);
+      if (rc != NBEST_OK) return rc;
+    }
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (BN == 256) return dispatch<256>(ctx, a_mn_major, b_mn_major, epilogue, tmA, tmB, g, s);
-  return dispatch<128>(ctx, a_mn_major, b_mn_major, epilogue, tmA, tmB, g, s);
+  if (BN == 256) return dispatch<256>(ctx, a_mn_major, b_mn_major, epilogue, tmA, tmB, tmC, tmC2, g, s);
+  return dispatch<128>(ctx, a_mn_major, b_mn_major, epilogue, tmA, tmB, tmC, tmC2, g, s);
 }

@@ -39,6 +39,8 @@ class GradBucketer:
         current stream; CPU (gloo): asynchronous work handle."""
         if self.world == 1:
             return
+        if name not in self.by_name:
+            return                                # a layer inside a merged bucket: its group is not complete yet
         s, e = self.by_name[name]
         buf = self.flat[s:e]
         if buf.is_cuda:
@@ -61,24 +63,27 @@ class GradBucketer:
         self._pending = []
 
 
-def model_segments(model):
-    """Bucket plan for a TOD_ASR_Transformer_STC: head | layer L-1 | ... | layer 0 | embeddings (pooler excluded)."""
+def model_segments(model, layers_per_bucket=None):
+    """Bucket plan for a TOD_ASR_Transformer_STC in the order backward finishes the gradients:
+    [head + pooler gap + top layers] | ... groups of `layers_per_bucket` layers ... | embeddings.
+    A bucket is named after the LAST layer of its group to finish (the lowest index), which is the name the model's
+    backward reports; the other layers of the group report names that are not buckets and are ignored. The pooler's
+    (always zero) gradient region lies inside the first span, which keeps every bucket one contiguous slice."""
+    if layers_per_bucket is None:
+        layers_per_bucket = int(os.environ.get("NBEST_BUCKET_LAYERS", "2"))
     f, idx = model.flat, model._index
-    names = model._names
+    L = model.spec.layers
 
-    def span(first, last):
-        i0, i1 = idx[first], idx[last]
-        end = f.offsets[i1] + int(torch.Size(f.shapes[i1]).numel())
-        return f.offsets[i0], end
+    def start(name):
+        return f.offsets[idx[name]]
 
-    segs = []
-    head_first = "clf.top_linear_layer.weight"
-    segs.append(("head",) + span(head_first, names[-1]))
-    for l in reversed(range(model.spec.layers)):
-        p = "bert_encoder.encoder.layer.%d." % l
-        segs.append(("layer%d" % l,) + span(p + "attention.self.query.weight", p + "output.LayerNorm.bias"))
-    e = "bert_encoder.embeddings."
-    segs.append(("emb",) + span(e + "word_embeddings.weight", e + "LayerNorm.bias"))
+    lay = lambda l: "bert_encoder.encoder.layer.%d.attention.self.query.weight" % l
+    segs, hi, end = [], L, f.total
+    while hi > 0:
+        lo = max(0, hi - layers_per_bucket)
+        segs.append(("layer%d" % lo, start(lay(lo)), end))
+        end, hi = start(lay(lo)), lo
+    segs.append(("emb", 0, end))
     return segs
 
 
