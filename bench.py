@@ -232,9 +232,10 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), ctx.launches() - l0, out
 
-    if world > 1:
-        for i in range(5):          # communicator bring-up (NVLS buffers, channel setup) before the W warm-up steps
-            step_dev(i)
+    # bring-up before the W warm-up steps: every distinct batch shape once (the caching allocator grows on first use and
+    # cudaMalloc synchronises), and the NCCL communicator (NVLS buffers, channel setup) when world > 1
+    for i in range(NB + (4 if world > 1 else 0)):
+        step_dev(i)
     for i in range(args.warmup):
         step_dev(i)
     sampler = ClockSampler(local) if rank == 0 else None

@@ -193,11 +193,17 @@ __device__ __forceinline__ void block_reduce_cols_atomic(float4 (&acc)[VPL], flo
 #pragma unroll
   for (int i = 0; i < VPL; ++i) *reinterpret_cast<float4*>(sh + warp * H + 4 * (lane + 32 * i)) = acc[i];
   __syncthreads();
-  for (int c = threadIdx.x; c < H; c += blockDim.x) {
-    float s = 0.f;
+  for (int c = 4 * threadIdx.x; c < H; c += 4 * blockDim.x) {   // one 4-wide vector reduction per thread
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int w = 0; w < kWarpsPerBlock; ++w) s += sh[w * H + c];
-    atomicAdd(out + c, s);
+    for (int w = 0; w < kWarpsPerBlock; ++w) {
+      const float4 v = *reinterpret_cast<const float4*>(sh + w * H + c);
+      s.x += v.x;
+      s.y += v.y;
+      s.z += v.z;
+      s.w += v.w;
+    }
+    red_add_v4(out + c, s);
   }
 }
 
@@ -248,15 +254,41 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dyin, const __nv_bfloat16* __res
   float4 dgam[VPL], dbet[VPL], dbia[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) dgam[i] = dbet[i] = dbia[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int t = blockIdx.x * kWarpsPerBlock + warp; t < T; t += gridDim.x * kWarpsPerBlock) {
-    const float mu = mean[t], rs = rstd[t];
-    float4 xhat[VPL], dy[VPL];
+  // software pipeline: the packed bf16 rows of the warp's NEXT token are in flight while the current one is reduced
+  // (the kernel runs at one block per SM because of its 72 column accumulators per lane, so memory-level parallelism
+  // has to come from inside the warp)
+  const int tstep = gridDim.x * kWarpsPerBlock;
+  int t = blockIdx.x * kWarpsPerBlock + warp;
+  uint2 nx[VPL], ndy[VPL];
+  float nmu = 0.f, nrs = 0.f;
+  if (t < T) {
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = 4 * (lane + 32 * i);
-      const float4 xv = bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(xin + (int64_t)t * H + c)));
+      nx[i] = __ldg(reinterpret_cast<const uint2*>(xin + (int64_t)t * H + c));
+      ndy[i] = __ldg(reinterpret_cast<const uint2*>(dyin + (int64_t)t * H + c));
+    }
+    nmu = mean[t];
+    nrs = rstd[t];
+  }
+  for (; t < T; t += tstep) {
+    const float mu = nmu, rs = nrs;
+    float4 xhat[VPL], dy[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float4 xv = bf16x4_to_f4(nx[i]);
       xhat[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-      dy[i] = bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(dyin + (int64_t)t * H + c)));
+      dy[i] = bf16x4_to_f4(ndy[i]);
+    }
+    if (t + tstep < T) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int c = 4 * (lane + 32 * i);
+        nx[i] = __ldg(reinterpret_cast<const uint2*>(xin + (int64_t)(t + tstep) * H + c));
+        ndy[i] = __ldg(reinterpret_cast<const uint2*>(dyin + (int64_t)(t + tstep) * H + c));
+      }
+      nmu = mean[t + tstep];
+      nrs = rstd[t + tstep];
     }
     ln_bwd_row(xhat, dy, rs, gamma, lane, dgam, dbet);
 #pragma unroll
@@ -347,12 +379,12 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int T, int N,
   const int r1 = min(r0 + rows_per_block, T);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   int r = r0;
-  for (; r + 4 <= r1; r += 4) {
-    uint2 v[4];
+  for (; r + 8 <= r1; r += 8) {   // 8 independent 8-byte loads in flight per thread
+    uint2 v[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const uint2*>(x + (int64_t)(r + k) * N + c));
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const uint2*>(x + (int64_t)(r + k) * N + c));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) f4_acc(acc, bf16x4_to_f4(v[k]));
+    for (int k = 0; k < 8; ++k) f4_acc(acc, bf16x4_to_f4(v[k]));
   }
   for (; r < r1; ++r) f4_acc(acc, bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(x + (int64_t)r * N + c))));
   red_add_v4(out + c, acc);
@@ -420,7 +452,7 @@ extern "C" int nbest_embed_ln_bwd(nbest_ctx* ctx, const int32_t* tokens, const u
   NBEST_CHECK_ARG(ctx, dword && dpos && dtype && dgamma && dbeta, "null gradient pointer");
   if (T <= 0) return NBEST_OK;
   int blocks = (T + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  if (blocks > 2 * ctx->num_sms) blocks = 2 * ctx->num_sms;
+  if (blocks > ctx->num_sms) blocks = ctx->num_sms;   // one block per SM (register-bound); fewer blocks = fewer column atomics
   embed_ln_bwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       tokens, seg, pos, T, word, posemb, type, gamma, mean, rstd, reinterpret_cast<const __nv_bfloat16*>(dy_bf16),
       drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed, dword, dpos, dtype, dgamma, dbeta, word_pad_row, pos_pad_row);
@@ -450,7 +482,7 @@ extern "C" int nbest_ln_bwd(nbest_ctx* ctx, const void* dy_bf16, const void* x_b
   NBEST_CHECK_ARG(ctx, !(p_drop > 0.f) || dx_masked_bf16, "p_drop > 0 needs dx_masked");
   if (T <= 0) return NBEST_OK;
   int blocks = (T + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  if (blocks > 2 * ctx->num_sms) blocks = 2 * ctx->num_sms;
+  if (blocks > ctx->num_sms) blocks = ctx->num_sms;   // one block per SM (register-bound); fewer blocks = fewer column atomics
   ln_bwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16), mean, rstd, gamma, T,
       reinterpret_cast<__nv_bfloat16*>(dx_bf16), p_drop > 0.f ? reinterpret_cast<__nv_bfloat16*>(dx_masked_bf16) : nullptr,
@@ -466,9 +498,9 @@ extern "C" int nbest_colsum_bf16(nbest_ctx* ctx, const void* x_bf16, int T, int 
   if (T <= 0) return NBEST_OK;
   const int threads = 128;
   const int gx = (N / 4 + threads - 1) / threads;
-  int gy = (4 * ctx->num_sms + gx - 1) / gx;
+  int gy = (8 * ctx->num_sms + gx - 1) / gx;
   int rows_per_block = (T + gy - 1) / gy;
-  if (rows_per_block < 16) rows_per_block = 16;
+  if (rows_per_block < 32) rows_per_block = 32;
   gy = (T + rows_per_block - 1) / rows_per_block;
   colsum_kernel<<<dim3(gx, gy), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x_bf16), T, N, rows_per_block, out);

@@ -462,6 +462,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
         self._encoder_backward(sv, dx, T_act, B_act)
 
     # ------------------------------------------------------------------------------------------------ public: drop-in forward
+    @ops.with_bound_stream
     def forward(self, opt, input_ids, trans_input_ids=None, seg_ids=None, trans_seg_ids=None, return_attns=False,
                 classifier_input_type="asr", input_lens=None, trans_input_lens=None):
         """Reference signature (models/model.py:35). Returns (top_scores [B,30], {'lin_k': [B,n_k]}, final_scores [B,161],
@@ -497,6 +498,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
         return top, bottoms, final, asr_cls, trans_cls
 
     # ------------------------------------------------------------------------------------------------ public: fused step
+    @ops.with_bound_stream
     def forward_loss_backward(self, input_ids, labels, trans_input_ids=None, seg_ids=None, trans_seg_ids=None,
                               add_l2_loss=False, mse_scale=1.0, input_lens=None, trans_input_lens=None, backward=True):
         """Fused training path: model forward + cal_total_loss (n_best_asr_bert.py:160-195) + backward in our kernels.
@@ -528,6 +530,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
         return losses, ho
 
     @torch.no_grad()
+    @ops.with_bound_stream
     def infer(self, input_ids, seg_ids=None, input_lens=None):
         """Inference step (eval_epoch, n_best_asr_bert.py:316-344): forward + decode bitmap, no activations kept."""
         was = self.training
@@ -553,6 +556,7 @@ class _STCFunction(torch.autograd.Function):
         return top.view_as(top), bottom.view_as(bottom), final.view_as(final), asr_cls.view_as(asr_cls), trans_cls.view_as(trans_cls)
 
     @staticmethod
+    @ops.with_bound_stream
     def backward(ctx, d_top, d_bottom, d_final, d_asr, d_trans):
         model, sv, ho = ctx.model, ctx.sv, ctx.ho
         top, bottom = ctx.saved_tensors

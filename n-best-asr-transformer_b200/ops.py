@@ -55,8 +55,39 @@ def _ctx(t):
     return _lib.context(t.device.index if t.device.index is not None else torch.cuda.current_device())
 
 
+_STREAM = None   # cached cudaStream_t of the stream the current step launches on (torch.cuda.current_stream() costs ~10 us)
+
+
+def bind_stream():
+    """Cache torch's current stream for the launches that follow. The model / trainer entry points call this once per
+    step; code that switches streams in between must call it again (or `unbind_stream()` to query torch every time)."""
+    global _STREAM
+    _STREAM = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def unbind_stream():
+    global _STREAM
+    _STREAM = None
+
+
+def with_bound_stream(fn):
+    """Decorator for the public entry points: bind the current stream once for all launches made inside."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        if _STREAM is not None:
+            return fn(*a, **k)
+        bind_stream()
+        try:
+            return fn(*a, **k)
+        finally:
+            unbind_stream()
+    return wrapper
+
+
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return _STREAM if _STREAM is not None else C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def _p(t):

@@ -179,6 +179,7 @@ class BertAdam(torch.optim.Optimizer):
                 for p, s, i in zip(self._plist, self._steps, self._idx)}
 
     @torch.no_grad()
+    @ops.with_bound_stream
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         groups = self._hyper()

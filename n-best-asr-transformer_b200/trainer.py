@@ -17,6 +17,8 @@ import os
 import torch
 import torch.distributed as dist
 
+from . import ops
+
 
 class GradBucketer:
     """Contiguous gradient buckets over a flat buffer + their (optionally asynchronous) SUM all-reduce.
@@ -120,6 +122,7 @@ class DataParallelTrainer:
         self.bucketer = GradBucketer(model.flat.grads, model_segments(model), group, self.comm_stream)
         self.group = group
 
+    @ops.with_bound_stream
     def step(self, ids, labels, trans_ids=None, seg=None, trans_seg=None, lens=None, trans_lens=None):
         m = self.model
         if self.comm_stream is not None:
