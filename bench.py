@@ -50,6 +50,16 @@ def peaks():
     return dict(hbm=6650.0, tf_sustained=1400.0, tf_burst=1590.0, src="fallback")
 
 
+def gemm_traffic():
+    """DRAM bytes (read + write) per GEMM launch, averaged over the 144 GEMM launches of one B = 256 training step, from
+    the committed ncu capture (profiles/r1_gemm_dram_traffic.txt); None when the capture is absent or the workload differs."""
+    p = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ CPU port (oracle)
 def cpu_port_step_time(n_utt, steps, warmup, seed=999, threads=None):
     """Times the oracle port of the reference training step (both streams, dropout on, fp32, BertAdam) on host cores."""
@@ -292,7 +302,7 @@ def main():
                      ms_per_step=ms_e2e / args.steps),
             gpu_launches=int(launches),
             roofline=dict(bound="tensor", kernel="gemm_kernel (tcgen05, all instances of one step)", achieved=achieved,
-                          peak=pk["tf_sustained"], unit="TFLOP/s", frac=achieved / pk["tf_sustained"], traffic=None,
+                          peak=pk["tf_sustained"], unit="TFLOP/s", frac=achieved / pk["tf_sustained"], traffic=gemm_traffic() if (args.batch == 256 and args.hyps == 5 and not args.dense and not args.l2) else None,
                           peak_source=pk["src"] + " bf16_tflops_sustained", gemm_ms_per_step=gemm_ms,
                           gemm_share_of_step=gemm_ms / (step_s * 1e3)),
             tc_util=dict(asr_stream_formula=alg / (step_s * pk["tf_sustained"] * 1e12),

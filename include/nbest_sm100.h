@@ -133,6 +133,18 @@ int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* c
                           const float* lse, void* dqkv_bf16, float* delta_ws, float p_drop, uint32_t seed,
                           void* stream);
 
+/* Last encoder layer: only the [CLS] row of each sequence is consumed downstream (models/model.py:46-47,58), so its
+ * attention is evaluated for that single query row. out_cls [B, heads*64] bf16, lse_cls [heads, B] fp32. Same
+ * arithmetic and the same dropout-mask indices as nbest_attn_varlen_fwd would use for row cu_seqlens[b]. max_len <= 512. */
+int nbest_attn_cls_fwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens, const uint8_t* key_valid, int B,
+                       int max_len, int heads, int T, void* out_cls_bf16, float* lse_cls, float p_drop, uint32_t seed,
+                       void* stream);
+/* Backward of the above for the first B sequences: writes ALL rows of dqkv [cu_seqlens[B], 3*heads*64] that belong to
+ * them (dQ = 0 except at the CLS rows). lse_cls has row pitch lse_stride (the forward's B). */
+int nbest_attn_cls_bwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens, const uint8_t* key_valid, int B,
+                       int max_len, int heads, int T, const void* out_cls_bf16, const void* dout_cls_bf16,
+                       const float* lse_cls, int lse_stride, void* dqkv_bf16, float p_drop, uint32_t seed, void* stream);
+
 /* ---- K8/K9/K10: CLS gather + hierarchical STC head + losses ----------------------------------------------- */
 /* Label hierarchy (memory['top2bottom_dict'], n_best_asr_bert.py:489-496) flattened by the host into int32 tables:
  *   n_top (30), n_bottom (161), n_groups (10 multi-way groups), n_cols = n_top + sum(n_k) (171)

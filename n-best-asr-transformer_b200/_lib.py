@@ -45,6 +45,9 @@ _SIGNATURES = {
     "nbest_attn_varlen_fwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32, _u32, _vp]),
     "nbest_attn_varlen_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp,
                                         _f32, _u32, _vp]),
+    "nbest_attn_cls_fwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32, _u32, _vp]),
+    "nbest_attn_cls_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp,
+                                     _f32, _u32, _vp]),
     "nbest_stc_head_fwd": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.POINTER(Hierarchy), _vp, _f32, _u32,
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nbest_stc_loss_fwd_bwd": (C.c_int, [_vp, _vp, _vp, C.c_int, C.POINTER(Hierarchy), _vp, _vp, C.c_int, _f32, _vp, _vp,

@@ -419,12 +419,17 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
   g.num_kb = (K + BK - 1) / BK;
   g.num_splits = 1;
   if (epilogue == NBEST_EPI_ACCUM_F32) {
-    // split the contraction so that (tiles x splits) covers about two waves of SMs, with >= 8 k-blocks per split
+    // split the contraction so that (tiles x splits) fills ONE wave of SMs (measured best on B200: e.g. 72 tiles x 2,
+    // 54 x 2, 18 x 8 — a second wave or more splits only add fp32 atomic traffic), with >= 8 k-blocks per split
     const int tiles = g.num_m_tiles * g.num_n_tiles;
-    int want = (2 * ctx->num_sms + tiles - 1) / tiles;
+    int want = ctx->num_sms / tiles;
     int max_by_k = g.num_kb / 8 > 0 ? g.num_kb / 8 : 1;
     if (want > max_by_k) want = max_by_k;
     if (want < 1) want = 1;
+    if (const char* sp = getenv("NBEST_WGRAD_SPLITS")) {
+      const int v = atoi(sp);
+      if (v >= 1) want = v < max_by_k ? v : max_by_k;
+    }
     g.num_splits = want;
   }
   g.debug = getenv("NBEST_GEMM_DEBUG") ? atoi(getenv("NBEST_GEMM_DEBUG")) : 0;

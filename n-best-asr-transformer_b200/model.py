@@ -131,6 +131,10 @@ class TOD_ASR_Transformer_STC(nn.Module):
         self.hier = ops.DeviceHierarchy(top2bottom, none_bottoms, device=device)
         self.top2bottom_dict = self.hier.top2bottom
         self._step_seed = int(seed)
+        # The head (and the MSE term) only ever read the [CLS] row of the last hidden state (reference models/model.py:
+        # 46-47,58), so the last layer's attention output, out-projection, FFN and LayerNorms are computed for that row
+        # only; identical results, ~1/12 less encoder work. False = run the last layer on every token.
+        self.cls_only_last_layer = True
         self._build_params(encoder_state, seed)
 
     # ------------------------------------------------------------------------------------------------ parameters
@@ -331,33 +335,57 @@ class TOD_ASR_Transformer_STC(nn.Module):
                          sv.rstd0, p_h, self._seed(0, 15))
         kv = pk.key_valid if s.kind == "xlm-roberta" else None     # BERT: every in-sequence key is valid (ids > 0)
         qkv = ctx = pre1 = x1 = u = gact = pre2 = None
+        cls_last = self.cls_only_last_layer and s.layers >= 1
+        sv.cls_compact = cls_last
         for l in range(s.layers):
             w = self._w[l]
             L = _Saved()
+            last_cls = cls_last and l == s.layers - 1
+            # rows that the post-attention block (out-proj .. LN2) works on: every token, or one [CLS] row per sequence in
+            # the last layer (only that row is consumed downstream: reference models/model.py:46-47,58)
+            n = pk.B if last_cls else T
             if save or qkv is None:
-                qkv, ctx, pre1, x1 = bf(T, 3 * H), bf(T, H), bf(T, H), bf(T, H)
-                u = bf(T, s.intermediate) if save else None
-                gact, pre2 = bf(T, s.intermediate), bf(T, H)
-            L.x_in = x
+                qkv = bf(T, 3 * H)
+            if save or ctx is None or ctx.shape[0] != n:
+                ctx, pre1, x1 = bf(n, H), bf(n, H), bf(n, H)
+                u = bf(n, s.intermediate) if save else None
+                gact, pre2 = bf(n, s.intermediate), bf(n, H)
+            L.x_in, L.n = x, n
             ops.gemm(x, w["h_wqkv"], epilogue=ops.EPI_BIAS, bias=w["p_bqkv"], out=qkv)
-            L.lse = f32(s.heads, T)
-            ops.attn_fwd(qkv, pk.cu_seqlens, kv, pk.B, pk.max_len, s.heads, T, ctx, L.lse, p_a, self._seed(l, 1))
-            ops.gemm(ctx, w["h_wo"], epilogue=ops.EPI_BIAS_DROP_RES, bias=w["p_bo"], aux=x, out=pre1, p_drop=p_h,
+            if last_cls:
+                L.lse = f32(s.heads, pk.B)
+                ops.attn_cls_fwd(qkv, pk.cu_seqlens, kv, pk.B, pk.max_len, s.heads, T, ctx, L.lse, p_a, self._seed(l, 1))
+                resid = x.index_select(0, pk.cu_seqlens[:pk.B].long())
+            else:
+                L.lse = f32(s.heads, T)
+                ops.attn_fwd(qkv, pk.cu_seqlens, kv, pk.B, pk.max_len, s.heads, T, ctx, L.lse, p_a, self._seed(l, 1))
+                resid = x
+            ops.gemm(ctx, w["h_wo"], epilogue=ops.EPI_BIAS_DROP_RES, bias=w["p_bo"], aux=resid, out=pre1, p_drop=p_h,
                      seed=self._seed(l, 2))
-            L.mean1, L.rstd1 = f32(T), f32(T)
+            L.mean1, L.rstd1 = f32(n), f32(n)
             ops.ln_fwd(pre1, w["p_g1"], w["p_b1"], s.ln_eps, x1, L.mean1, L.rstd1)
             ops.gemm(x1, w["h_w1"], epilogue=ops.EPI_BIAS_GELU, bias=w["p_bi"], out=gact, out2=u)
             ops.gemm(gact, w["h_w2"], epilogue=ops.EPI_BIAS_DROP_RES, bias=w["p_b2o"], aux=x1, out=pre2, p_drop=p_h,
                      seed=self._seed(l, 3))
-            L.mean2, L.rstd2 = f32(T), f32(T)
-            x_out = bf(T, H) if save else self._pingpong(x, T)
+            L.mean2, L.rstd2 = f32(n), f32(n)
+            x_out = bf(n, H) if (save or last_cls) else self._pingpong(x, T)
             ops.ln_fwd(pre2, w["p_g2"], w["p_b2"], s.ln_eps, x_out, L.mean2, L.rstd2)
             L.qkv, L.ctx, L.pre1, L.x1, L.u, L.g, L.pre2 = qkv, ctx, pre1, x1, u, gact, pre2
             if save:
                 sv.layers.append(L)
             x = x_out
-        sv.x_last = x
+        sv.x_last = x            # [T,768], or [B,768] (row b = sequence b) when the last layer ran on the CLS rows only
         return sv
+
+    def _cls_cu(self, sv, row0, B):
+        """cu_seqlens-style row index of the CLS vectors of sequences row0 .. row0+B inside sv.x_last."""
+        if sv.cls_compact:
+            ar = getattr(self, "_arange_i32", None)
+            if ar is None or ar.numel() < sv.pk.B + 1:
+                ar = torch.arange(max(1024, sv.pk.B + 1), device=self.device, dtype=torch.int32)
+                self._arange_i32 = ar
+            return ar[row0:row0 + B + 1]
+        return sv.pk.cu_seqlens[row0:row0 + B + 1]
 
     def _pingpong(self, x, T):
         """Inference: two alternating hidden-state buffers instead of one per layer."""
@@ -378,30 +406,44 @@ class TOD_ASR_Transformer_STC(nn.Module):
         kv = pk.key_valid if s.kind == "xlm-roberta" else None
         cu = pk.cu_seqlens[:B_act + 1]
         max_len = pk.max_len_asr if B_act == pk.B_asr and B_act != pk.B else pk.max_len
-        dpre, dprem = bf(T_act, H), (bf(T_act, H) if p_h > 0 else None)
-        du, dx1, dctx, dqkv = bf(T_act, s.intermediate), bf(T_act, H), bf(T_act, H), bf(T_act, 3 * H)
+        dqkv = bf(T_act, 3 * H)
         delta = torch.empty((s.heads, T), device=dev, dtype=torch.float32)
         A = lambda t: t[:T_act]
+        ws = {}       # per-row-count workspaces of the post-attention block: {n: (dpre, dprem, du, dx1, dctx)}
         for l in reversed(range(s.layers)):
             w, L = self._w[l], sv.layers[l]
+            compact = sv.cls_compact and l == s.layers - 1       # this layer's tail ran on one CLS row per sequence
+            n = B_act if compact else T_act
+            if n not in ws:
+                ws[n] = (bf(n, H), (bf(n, H) if p_h > 0 else None), bf(n, s.intermediate), bf(n, H), bf(n, H))
+            dpre, dprem, du, dx1, dctx = ws[n]
+            R = lambda t: t[:n]
             # ---- FFN block
-            ops.ln_bwd(dx, A(L.pre2), L.mean2, L.rstd2, w["p_g2"], dpre, w["g_g2"], w["g_b2"], dx_masked=dprem,
-                       dbias=w["g_b2o"], p_drop=p_h, seed=self._seed(l, 3), T=T_act)
+            ops.ln_bwd(dx, R(L.pre2), L.mean2, L.rstd2, w["p_g2"], dpre, w["g_g2"], w["g_b2"], dx_masked=dprem,
+                       dbias=w["g_b2o"], p_drop=p_h, seed=self._seed(l, 3), T=n)
             dm = dprem if p_h > 0 else dpre
-            ops.gemm(dm, w["h_w2"], b_mn_major=True, epilogue=ops.EPI_DGELU, aux=A(L.u), out=du)           # du = (dm W2) * gelu'(u)
-            ops.gemm(dm, A(L.g), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_w2"])
+            ops.gemm(dm, w["h_w2"], b_mn_major=True, epilogue=ops.EPI_DGELU, aux=R(L.u), out=du)           # du = (dm W2) * gelu'(u)
+            ops.gemm(dm, R(L.g), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_w2"])
             ops.gemm(du, w["h_w1"], b_mn_major=True, epilogue=ops.EPI_ADD, aux=dpre, out=dx1)              # + residual grad
-            ops.gemm(du, A(L.x1), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_w1"])
-            ops.colsum(du, w["g_bi"], T=T_act)
+            ops.gemm(du, R(L.x1), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_w1"])
+            ops.colsum(du, w["g_bi"], T=n)
             # ---- attention block
-            ops.ln_bwd(dx1, A(L.pre1), L.mean1, L.rstd1, w["p_g1"], dpre, w["g_g1"], w["g_b1"], dx_masked=dprem,
-                       dbias=w["g_bo"], p_drop=p_h, seed=self._seed(l, 2), T=T_act)
+            ops.ln_bwd(dx1, R(L.pre1), L.mean1, L.rstd1, w["p_g1"], dpre, w["g_g1"], w["g_b1"], dx_masked=dprem,
+                       dbias=w["g_bo"], p_drop=p_h, seed=self._seed(l, 2), T=n)
             dm = dprem if p_h > 0 else dpre
             ops.gemm(dm, w["h_wo"], b_mn_major=True, epilogue=ops.EPI_NONE, out=dctx)
-            ops.gemm(dm, A(L.ctx), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_wo"])
-            ops.attn_bwd(L.qkv, cu, kv, B_act, max_len, s.heads, T, L.ctx, dctx, L.lse, dqkv, delta, p_a, self._seed(l, 1),
-                         T_active=T_act)
-            ops.gemm(dqkv, w["h_wqkv"], b_mn_major=True, epilogue=ops.EPI_ADD, aux=dpre, out=dx)   # dx was consumed above
+            ops.gemm(dm, R(L.ctx), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_wo"])
+            if compact:
+                ops.attn_cls_bwd(L.qkv, cu, kv, B_act, max_len, s.heads, T, L.ctx, dctx, L.lse, pk.B, dqkv, p_a, self._seed(l, 1))
+                # the residual branch reaches the layer input only at the CLS rows
+                dres = torch.zeros((T_act, H), device=dev, dtype=torch.bfloat16)
+                dres.index_copy_(0, cu[:B_act].long(), dpre)
+                dx = bf(T_act, H)
+            else:
+                ops.attn_bwd(L.qkv, cu, kv, B_act, max_len, s.heads, T, L.ctx, dctx, L.lse, dqkv, delta, p_a, self._seed(l, 1),
+                             T_active=T_act)
+                dres = dpre
+            ops.gemm(dqkv, w["h_wqkv"], b_mn_major=True, epilogue=ops.EPI_ADD, aux=dres, out=dx)   # (full path: dx was consumed above)
             ops.gemm(dqkv, A(L.x_in), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_wqkv"])
             ops.colsum(dqkv, w["g_bqkv"], T=T_act)
             self._notify("layer%d" % l)
@@ -427,11 +469,13 @@ class TOD_ASR_Transformer_STC(nn.Module):
         o.decode = torch.empty((B, hier.n_bottom), device=dev, dtype=torch.uint8)
         o.p = self.head_dropout if self.training else 0.0
         o.seed = self._seed(99, 7)
-        ops.stc_head_fwd(sv.x_last, sv.pk.cu_seqlens[row0:row0 + B + 1], B, self._head["p_w"], self._head["p_b"], hier, o.cls,
+        ops.stc_head_fwd(sv.x_last, self._cls_cu(sv, row0, B), B, self._head["p_w"], self._head["p_b"], hier, o.cls,
                          o.logits, o.top, o.bottom, o.final, o.decode, o.p, o.seed)
         return o
 
     def _cls_rows(self, sv, row0, B):
+        if sv.cls_compact:
+            return sv.x_last[row0:row0 + B].float()
         idx = sv.pk.cu_seqlens[row0:row0 + B].long()
         return sv.x_last.index_select(0, idx).float()
 
@@ -457,8 +501,12 @@ class TOD_ASR_Transformer_STC(nn.Module):
             if d_asr is None:
                 return
             dcls, T_act, B_act = d_asr, pk.T_asr, B
-        dx = torch.empty((T_act, H), device=dev, dtype=torch.bfloat16)
-        ops.cls_scatter(dcls.contiguous(), pk.cu_seqlens, B_act, T_act, dx)
+        if sv.cls_compact:       # gradient of the compact [B,768] last hidden state: row b = sequence b
+            dx = torch.empty((B_act, H), device=dev, dtype=torch.bfloat16)
+            ops.cls_scatter(dcls.contiguous(), self._cls_cu(sv, 0, B_act), B_act, B_act, dx)
+        else:
+            dx = torch.empty((T_act, H), device=dev, dtype=torch.bfloat16)
+            ops.cls_scatter(dcls.contiguous(), pk.cu_seqlens, B_act, T_act, dx)
         self._encoder_backward(sv, dx, T_act, B_act)
 
     # ------------------------------------------------------------------------------------------------ public: drop-in forward

@@ -236,6 +236,23 @@ def attn_bwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out, dout, lse, d
                                                    _stream()))
 
 
+def attn_cls_fwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out_cls, lse_cls, p_drop=0.0, seed=0):
+    """Last-layer attention for the CLS query row of each of the B sequences (see nbest_attn_cls_fwd)."""
+    ctx = _ctx(qkv)
+    with _Timed('attn_cls_fwd', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_attn_cls_fwd(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
+                                                _p(out_cls), _p(lse_cls), float(p_drop), _seed(seed), _stream()))
+
+
+def attn_cls_bwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out_cls, dout_cls, lse_cls, lse_stride, dqkv, p_drop=0.0,
+                 seed=0):
+    ctx = _ctx(qkv)
+    with _Timed('attn_cls_bwd', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_attn_cls_bwd(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
+                                                _p(out_cls), _p(dout_cls), _p(lse_cls), lse_stride, _p(dqkv), float(p_drop),
+                                                _seed(seed), _stream()))
+
+
 # ---------------------------------------------------------------------------------------------------------- STC head / loss
 class DeviceHierarchy:
     """Label hierarchy tables on the device + the ctypes struct the C ABI takes (nbest_hierarchy)."""

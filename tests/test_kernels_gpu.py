@@ -289,6 +289,56 @@ def test_attention_dropout_forward_backward_consistent():
     assert abs(fd - an) / abs(an) < 0.08
 
 
+@pytest.mark.parametrize("lens", [[1, 17, 64, 65, 128], [200, 3, 512, 129], [46] * 9])
+def test_attention_cls_row_matches_full_kernel_and_reference(lens):
+    """Last-layer shortcut (reference models/model.py:46-47 keeps only the [CLS] row): the one-query kernels must
+    reproduce row cu[b] of the full attention — same dropout mask included — and its backward must equal the full
+    backward fed with a dO that is zero outside the CLS rows."""
+    from nbest_b200 import ops
+    heads, B = 12, len(lens)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    T = int(cu[-1])
+    g = torch.Generator(device="cuda").manual_seed(7 + sum(lens))
+    qkv = (torch.randn(T, 3 * heads * 64, device="cuda", generator=g) * 1.2).to(torch.bfloat16)
+    key_valid = torch.ones(T, dtype=torch.uint8, device="cuda")
+    for b in range(B):
+        if lens[b] > 4:
+            key_valid[int(cu[b])] = 0 if b % 2 else 1
+            key_valid[int(cu[b]) + 3] = 0
+    cu_d = torch.from_numpy(cu).cuda()
+    rows = cu_d[:B].long()
+    dout_cls = torch.randn(B, heads * 64, device="cuda", generator=g).to(torch.bfloat16)
+    dout_full = torch.zeros(T, heads * 64, device="cuda", dtype=torch.bfloat16)
+    dout_full[rows] = dout_cls
+    for p, seed in [(0.0, 0), (0.25, 4242)]:
+        out = torch.empty(T, heads * 64, device="cuda", dtype=torch.bfloat16)
+        lse = torch.empty(heads, T, device="cuda")
+        ops.attn_fwd(qkv, cu_d, key_valid, B, max(lens), heads, T, out, lse, p_drop=p, seed=seed)
+        out_cls = torch.empty(B, heads * 64, device="cuda", dtype=torch.bfloat16)
+        lse_cls = torch.empty(heads, B, device="cuda")
+        ops.attn_cls_fwd(qkv, cu_d, key_valid, B, max(lens), heads, T, out_cls, lse_cls, p_drop=p, seed=seed)
+        assert _rel(out_cls, out[rows]) < 1e-2
+        assert _rel(lse_cls, lse[:, rows]) < 1e-4
+        dqkv = torch.empty_like(qkv)
+        ops.attn_bwd(qkv, cu_d, key_valid, B, max(lens), heads, T, out, dout_full, lse, dqkv,
+                     torch.empty(heads, T, device="cuda"), p_drop=p, seed=seed)
+        dqkv_cls = torch.full_like(qkv, float("nan"))
+        ops.attn_cls_bwd(qkv, cu_d, key_valid, B, max(lens), heads, T, out_cls, dout_cls, lse_cls, B, dqkv_cls, p_drop=p,
+                         seed=seed)
+        assert torch.isfinite(dqkv_cls.float()).all()               # every row of the B sequences is written
+        assert _rel(dqkv_cls, dqkv) < 2e-2 and _cos(dqkv_cls, dqkv) > 0.9995
+        if p == 0.0:
+            ref_out, ref_grads = _attn_ref(qkv, cu, key_valid, heads, dout_full)
+            assert _rel(out_cls, ref_out[rows.cpu()]) < 1e-2
+            assert _rel(dqkv_cls, ref_grads) < 2e-2 and _cos(dqkv_cls, ref_grads) > 0.9995
+    # a prefix of the sequences only (the no-l2 backward touches the ASR prefix): rows of later sequences stay untouched
+    Bp = max(1, B - 1)
+    part = torch.full_like(qkv, 3.0)
+    ops.attn_cls_bwd(qkv, cu_d, key_valid, Bp, max(lens), heads, T, out_cls, dout_cls, lse_cls, B, part, p_drop=p, seed=seed)
+    assert torch.all(part[int(cu[Bp]):] == 3.0)
+    assert torch.equal(part[:int(cu[Bp])], dqkv_cls[:int(cu[Bp])])
+
+
 # ------------------------------------------------------------------------------------------------------------ head + loss
 def _head_setup(B=9, seed=0):
     from nbest_b200 import ops

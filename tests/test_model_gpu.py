@@ -243,3 +243,32 @@ def test_dropout_training_step_is_finite_and_seeded():
     l2, _ = model.forward_loss_backward(d("ids"), d("labels"), d("trans_ids"), d("seg"), d("trans_seg"), add_l2_loss=True,
                                         backward=False)
     assert not torch.equal(l2, res[0][0])                     # dropout really was active in train mode
+
+
+@pytest.mark.parametrize("l2", [True, False])
+def test_cls_only_last_layer_equals_full_last_layer(l2):
+    """The last encoder layer's post-attention block runs on the [CLS] rows only (reference models/model.py:46-47,58 drop
+    every other row). With the same seeds (dropout ON) it must give the scores, losses and gradients of the full path."""
+    from oracle import stc_oracle as O
+    from nbest_b200.synth import synth_batch
+    hier_o, hj = _hier()
+    cfg = O.EncoderConfig.bert_base(layers=2, vocab_size=3000)
+    params = O.init_params(cfg, hier_o, seed=61, style="perturbed")
+    batch = synth_batch(cfg.kind, cfg.vocab_size, hier_o, B=10, n_hyps=5, max_len=128, seed=9)
+    d = lambda k: batch[k].cuda()
+    res = []
+    for compact in (True, False):
+        model = _build(cfg, hier_o, hj, params, dropout=0.3, hidden_dropout=0.1, attn_dropout=0.1)
+        model.cls_only_last_layer = compact
+        model.train()
+        model.zero_grad()
+        losses, ho = model.forward_loss_backward(d("ids"), d("labels"), d("trans_ids"), d("seg"), d("trans_seg"), add_l2_loss=l2)
+        res.append((losses.clone(), ho.top.clone(), ho.final.clone(), ho.cls.clone(),
+                    {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+    a, b = res
+    assert _rel(a[0], b[0]) < 2e-3 and _rel(a[1], b[1]) < 5e-3 and _rel(a[2], b[2]) < 5e-3 and _rel(a[3], b[3]) < 1e-2
+    assert a[4].keys() == b[4].keys()
+    for n in a[4]:
+        if "key.bias" in n:
+            continue
+        assert _cos(a[4][n], b[4][n]) > 0.9995, (n, _cos(a[4][n], b[4][n]))
