@@ -5,6 +5,13 @@
 // BertIntermediate.dense + GELU (:339-342), BertOutput.dense (:352-356), and their autograd products
 // (dgrad / wgrad of n_best_asr_bert.py:264 `total_loss.backward()`).
 //
+// CG = 2 (default): CTA PAIRS. The two CTAs of a cluster (one per SM of a TPC) compute a 256 x BN tile with
+// tcgen05.mma.cta_group::2: each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows), the leader CTA
+// (cluster rank 0) issues the MMAs for the pair, and each CTA's TMEM receives its 128 accumulator rows. Per MMA that is
+// 1.5x less shared-memory operand traffic and 1.5x less L2->SM traffic than two independent 128 x BN tiles — the two
+// limits (128 B/clk/SM smem, ~6.3 KB/clk chip-wide L2) that held the single-CTA kernel at ~67 % tensor-pipe activity.
+// CG = 1 keeps the single-CTA variant (NBEST_GEMM_CTA_GROUP=1) for A/B measurements.
+//
 // One CTA per SM (320 threads): warps 0..7 = epilogue (two warps per TMEM lane quarter, each owning 64-column units
 // that leave through TMA stores), warp 8 = TMA producer, warp 9 = TMEM owner + single-thread tcgen05.mma issuer (the issuers have
 // the highest warp ids so the scheduler never parks them behind busy epilogue warps). Tiles are 128 x BN (BN = 256 or 128) x 64, the smem ring has
@@ -49,15 +56,18 @@ struct GemmArgs {
   uint32_t seed;
 };
 
-template <int BN>
+template <int BN, int CG>
 struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
-  static constexpr uint32_t kABytes = BM * BK * 2;
-  static constexpr uint32_t kBBytes = BN * BK * 2;
+  static constexpr uint32_t kABytes = BM * BK * 2;               // per CTA: its own 128 rows of A
+  static constexpr uint32_t kBBytes = (BN / CG) * BK * 2;        // per CTA: BN / CG rows of B
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kStagingBytes = kEpiWarps * 4096;  // per epilogue warp: one 32-row x 128-byte store unit
-  static constexpr uint32_t kBarOffset = kStages * kStageBytes + kStagingBytes;
-  static constexpr uint32_t kSmemBytes = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int kStages = (CG == 2) ? ((BN == 256) ? 6 : 8) : ((BN == 256) ? 4 : 6);   // 192 KiB of operand ring
+  // per epilogue warp: one 32-row x 128-byte store unit. (Two alternating units per warp, with wait_group.read 1, were
+  // measured: no gain — the epilogues are not waiting for the store engine — and they cost a pipeline stage.)
+  static constexpr uint32_t kStagingBytes = kEpiWarps * 4096;
+  static constexpr uint32_t kBiasBytes = 2 * BN * 4;   // the tile's bias slice, double buffered by tile parity
+  static constexpr uint32_t kBarOffset = kStages * kStageBytes + kStagingBytes + kBiasBytes;
+  static constexpr uint32_t kSmemBytes = kBarOffset + 256;   // + barriers; the dynamic window itself is 1024-byte aligned
   static constexpr uint32_t kTmemCols = 2 * BN;
 };
 
@@ -65,14 +75,15 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, int CG, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmArgs g) {
-  using C_ = Cfg<BN>;
+  using C_ = Cfg<BN, CG>;
   constexpr int kStages = C_::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // SWIZZLE_128B operand tiles need 1024-byte alignment; the window starts at the same offset in both CTAs of a pair
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* staging = smem + kStages * C_::kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C_::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
@@ -82,6 +93,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;   // 0 = leader of the pair
+  const int unit = blockIdx.x / CG;                           // persistent work unit: a CTA (CG = 1) or a CTA pair
+  const int num_units = gridDim.x / CG;
   const int num_work = g.num_m_tiles * g.num_n_tiles * g.num_splits;
 
   if (warp == kProducerWarp && lane == 0) {
@@ -89,33 +103,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmB);
     if constexpr (EPI != NBEST_EPI_ACCUM_F32) tma_prefetch_desc(&tmC);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], 1);    // pair mode: only the leader's is used; it collects the bytes of BOTH CTAs' loads
+      mbar_init(&empty_bar[s], 1);   // arrived by tcgen05.commit (multicast to both CTAs in pair mode)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], kEpiWarps);
+      mbar_init(&tempty_bar[a], kEpiWarps * CG);   // pair mode: the leader's collects both CTAs' epilogue warps
     }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
-    tmem_alloc(tmem_slot, C_::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_cg2(tmem_slot, C_::kTmemCols);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, C_::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer
     uint32_t stage = 0, phase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    for (int w = unit; w < num_work; w += num_units) {
       const int num_tiles = g.num_m_tiles * g.num_n_tiles;   // tile fastest: concurrent CTAs share one T-range (L2 reuse)
       const int split = w / num_tiles;
       const int tile = w % num_tiles;
-      const int m0 = (tile / g.num_n_tiles) * BM;
-      const int n0 = (tile % g.num_n_tiles) * BN;
+      const int m0 = (tile / g.num_n_tiles) * (BM * CG) + (int)rank * BM;            // this CTA's 128 rows of A / D
+      const int nb0 = (tile % g.num_n_tiles) * BN + (int)rank * (BN / CG);           // this CTA's BN / CG rows of B
       const int kb0 = split * g.kb_per_split;
       const int kb1 = min(kb0 + g.kb_per_split, g.num_kb);
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -123,18 +143,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) {
           uint8_t* sa = smem + stage * C_::kStageBytes;
           uint8_t* sb = sa + C_::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], C_::kStageBytes);
+          // pair mode: both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], C_::kStageBytes * CG);
+          const uint32_t bar = (CG == 2) ? mapa_shared(smem_u32(&full_bar[stage]), 0) : 0u;
+          auto load = [&](const CUtensorMap* tm, uint8_t* dst, int c0, int c1) {
+            if constexpr (CG == 2) tma_load_2d_cg2(tm, bar, dst, c0, c1);
+            else tma_load_2d(tm, &full_bar[stage], dst, c0, c1);
+          };
           if constexpr (!A_MN) {
-            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m0);
+            load(&tmA, sa, kb * BK, m0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(&tmA, &full_bar[stage], sa + c * kChunkBytes, m0 + c * 64, kb * BK);
+            for (int c = 0; c < BM / 64; ++c) load(&tmA, sa + c * kChunkBytes, m0 + c * 64, kb * BK);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+            load(&tmB, sb, kb * BK, nb0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(&tmB, &full_bar[stage], sb + c * kChunkBytes, n0 + c * 64, kb * BK);
+            for (int c = 0; c < BN / CG / 64; ++c) load(&tmB, sb + c * kChunkBytes, nb0 + c * 64, kb * BK);
           }
         }
         __syncwarp();
@@ -145,12 +171,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    // ------------------------------------------------------------------ MMA issuer (pair mode: the leader CTA only)
+    constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     constexpr uint32_t a_lbo = A_MN ? kChunkBytes : 16, b_lbo = B_MN ? kChunkBytes : 16;
     constexpr uint32_t a_kstep = A_MN ? 2048 : 32, b_kstep = B_MN ? 2048 : 32;  // bytes per UMMA_K = 16
     uint32_t stage = 0, phase = 0, it = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+    if (rank == 0) {
+    for (int w = unit; w < num_work; w += num_units, ++it) {
       const int split = w / (g.num_m_tiles * g.num_n_tiles);
       const int kb0 = split * g.kb_per_split;
       const int kb1 = min(kb0 + g.kb_per_split, g.num_kb);
@@ -168,10 +195,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adesc = umma_smem_desc(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = umma_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CG == 2) umma_bf16_cg2(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                 // frees the smem slot once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+          if constexpr (CG == 2) {
+            umma_commit_cg2(&empty_bar[stage], 3);                  // frees the slot in BOTH CTAs once these MMAs retire
+            if (kb == kb1 - 1) umma_commit_cg2(&tfull_bar[acc], 3);   // accumulator complete -> both CTAs' epilogues
+          } else {
+            umma_commit(&empty_bar[stage]);                 // frees the smem slot once these MMAs retire
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
         if (++stage == (uint32_t)g.stages) {
@@ -179,6 +212,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           phase ^= 1;
         }
       }
+    }
     }
   } else {
     // ------------------------------------------------------------------ epilogue
@@ -189,11 +223,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp & 3;
     const int u_first = warp >> 2;
     uint8_t* st = staging + warp * 4096;
+    float* bias_tile = reinterpret_cast<float*>(staging + C_::kStagingBytes);
+    constexpr bool kHasBias = (EPI == NBEST_EPI_BIAS || EPI == NBEST_EPI_BIAS_GELU || EPI == NBEST_EPI_BIAS_DROP_RES);
     auto unit_off = [](int row, int chunk16) { return row * 128 + ((chunk16 ^ (row & 7)) << 4); };
     uint32_t it = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+    const uint32_t tempty_remote[2] = {(CG == 2) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u,
+                                       (CG == 2) ? mapa_shared(smem_u32(&tempty_bar[1]), 0) : 0u};
+    for (int w = unit; w < num_work; w += num_units, ++it) {
       const int tile = w % (g.num_m_tiles * g.num_n_tiles);
-      const int m0 = (tile / g.num_n_tiles) * BM;
+      const int m0 = (tile / g.num_n_tiles) * (BM * CG) + (int)rank * BM;   // this CTA's 128 accumulator rows
       const int n0 = (tile % g.num_n_tiles) * BN;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int row = m0 + q * 32 + lane;  // the accumulator row this thread owns
@@ -209,7 +247,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       };
       if constexpr (kHasAux) load_aux(2 * u_first);
+      // this warp's slice of the tile's bias (its own <= two 64-column units; the four warps of a unit write identical
+      // values): the global load is issued before the accumulator wait so that its latency hides behind the MMAs, the
+      // epilogue then reads it with short-latency broadcast LDS instead of stalling every chunk on global loads
+      float* bias_s = bias_tile + acc * BN;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int ub = u_first + 2 * (lane >> 4);
+      if constexpr (kHasBias) {
+        if (ub < BN / 64) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + ub * 64 + (lane & 15) * 4));
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
+      if constexpr (kHasBias) {
+        // safe to overwrite buffer `acc` now: this tile's MMAs only started after every epilogue warp released the
+        // accumulator (and with it the bias buffer) of the tile two iterations ago
+        if (ub < BN / 64) *reinterpret_cast<float4*>(bias_s + ub * 64 + (lane & 15) * 4) = b4;
+        __syncwarp();
+      }
       tc_fence_after();
       if constexpr (EPI == NBEST_EPI_ACCUM_F32) {
 #pragma unroll 1
@@ -263,10 +316,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               float v[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-              if constexpr (EPI == NBEST_EPI_BIAS || EPI == NBEST_EPI_BIAS_GELU || EPI == NBEST_EPI_BIAS_DROP_RES) {
+              if constexpr (kHasBias) {
+                const float* bsrc = bias_s + c * 32;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + nc + j));
+                  const float4 b = *reinterpret_cast<const float4*>(bsrc + j);
                   v[j] += b.x;
                   v[j + 1] += b.y;
                   v[j + 2] += b.z;
@@ -325,55 +379,87 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(tempty_remote[acc]);   // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(&tempty_bar[acc]);
+      }
     }
     if (lane == 0) bulk_wait_all();   // every bulk store of this warp is globally complete before the CTA exits
   }
 
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  // pair mode: neither CTA may exit (or free TMEM) while the peer can still read its smem / signal its barriers
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C_::kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, C_::kTmemCols);
+    else tmem_dealloc(tmem_base, C_::kTmemCols);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, int CG, bool A_MN, bool B_MN, int EPI>
 int launch(nbest_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
            const GemmArgs& g, cudaStream_t stream) {
-  auto kfn = gemm_kernel<BN, A_MN, B_MN, EPI>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    NBEST_CHECK_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
-    attr_done = true;
+  auto kfn = gemm_kernel<BN, CG, A_MN, B_MN, EPI>;
+  using C_ = Cfg<BN, CG>;
+  static int max_units = 0;  // per instantiation: CTAs (CG = 1) or co-resident CTA pairs (CG = 2)
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C_::kSmemBytes;
+  cfg.stream = stream;
+  if (CG == 2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  if (max_units == 0) {
+    NBEST_CHECK_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::kSmemBytes));
+    if (CG == 2) {
+      cfg.gridDim = dim3(ctx->num_sms / 2 * 2);
+      int n = 0;
+      NBEST_CHECK_CUDA(ctx, cudaOccupancyMaxActiveClusters(&n, kfn, &cfg));
+      if (n < 1) {
+        nbest_set_error(ctx, "nbest_gemm_bf16: no CTA pair of %u bytes of shared memory fits on this device", C_::kSmemBytes);
+        return NBEST_ECUDA;
+      }
+      max_units = n < ctx->num_sms / 2 ? n : ctx->num_sms / 2;
+    } else {
+      max_units = ctx->num_sms;
+    }
   }
   const int num_work = g.num_m_tiles * g.num_n_tiles * g.num_splits;
-  const int grid = num_work < ctx->num_sms ? num_work : ctx->num_sms;
-  kfn<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, g);
+  const int units = num_work < max_units ? num_work : max_units;
+  cfg.gridDim = dim3(units * CG);
+  NBEST_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, tmC, tmC2, g));
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
 
-template <int BN>
+template <int BN, int CG>
 int dispatch(nbest_ctx* ctx, int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
              const CUtensorMap& tmC, const CUtensorMap& tmC2, const GemmArgs& g, cudaStream_t s) {
   if (!a_mn && !b_mn) {
     switch (epi) {
-      case NBEST_EPI_NONE: return launch<BN, false, false, NBEST_EPI_NONE>(ctx, tmA, tmB, tmC, tmC2, g, s);
-      case NBEST_EPI_BIAS: return launch<BN, false, false, NBEST_EPI_BIAS>(ctx, tmA, tmB, tmC, tmC2, g, s);
-      case NBEST_EPI_BIAS_GELU: return launch<BN, false, false, NBEST_EPI_BIAS_GELU>(ctx, tmA, tmB, tmC, tmC2, g, s);
-      case NBEST_EPI_BIAS_DROP_RES: return launch<BN, false, false, NBEST_EPI_BIAS_DROP_RES>(ctx, tmA, tmB, tmC, tmC2, g, s);
+      case NBEST_EPI_NONE: return launch<BN, CG, false, false, NBEST_EPI_NONE>(ctx, tmA, tmB, tmC, tmC2, g, s);
+      case NBEST_EPI_BIAS: return launch<BN, CG, false, false, NBEST_EPI_BIAS>(ctx, tmA, tmB, tmC, tmC2, g, s);
+      case NBEST_EPI_BIAS_GELU: return launch<BN, CG, false, false, NBEST_EPI_BIAS_GELU>(ctx, tmA, tmB, tmC, tmC2, g, s);
+      case NBEST_EPI_BIAS_DROP_RES: return launch<BN, CG, false, false, NBEST_EPI_BIAS_DROP_RES>(ctx, tmA, tmB, tmC, tmC2, g, s);
       default: break;
     }
   } else if (!a_mn && b_mn) {
     switch (epi) {
-      case NBEST_EPI_NONE: return launch<BN, false, true, NBEST_EPI_NONE>(ctx, tmA, tmB, tmC, tmC2, g, s);
-      case NBEST_EPI_DGELU: return launch<BN, false, true, NBEST_EPI_DGELU>(ctx, tmA, tmB, tmC, tmC2, g, s);
-      case NBEST_EPI_ADD: return launch<BN, false, true, NBEST_EPI_ADD>(ctx, tmA, tmB, tmC, tmC2, g, s);
+      case NBEST_EPI_NONE: return launch<BN, CG, false, true, NBEST_EPI_NONE>(ctx, tmA, tmB, tmC, tmC2, g, s);
+      case NBEST_EPI_DGELU: return launch<BN, CG, false, true, NBEST_EPI_DGELU>(ctx, tmA, tmB, tmC, tmC2, g, s);
+      case NBEST_EPI_ADD: return launch<BN, CG, false, true, NBEST_EPI_ADD>(ctx, tmA, tmB, tmC, tmC2, g, s);
       default: break;
     }
   } else if (a_mn && b_mn) {
-    if (epi == NBEST_EPI_ACCUM_F32) return launch<BN, true, true, NBEST_EPI_ACCUM_F32>(ctx, tmA, tmB, tmC, tmC2, g, s);
+    if (epi == NBEST_EPI_ACCUM_F32) return launch<BN, CG, true, true, NBEST_EPI_ACCUM_F32>(ctx, tmA, tmB, tmC, tmC2, g, s);
   }
   nbest_set_error(ctx, "nbest_gemm_bf16: unsupported (a_mn_major=%d, b_mn_major=%d, epilogue=%d) combination", a_mn, b_mn,
                   epi);
@@ -400,11 +486,16 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
   NBEST_CHECK_ARG(ctx, !needs_aux || (aux_bf16 && ldaux % 8 == 0), "epilogue needs aux with ldaux % 8 == 0");
   NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
 
-  // 128 x 256 tiles halve the smem operand traffic per MMA; short-K problems with few tiles (out-proj: N = K = 768)
-  // prefer 128 x 128 so that the persistent CTAs see more, shorter tiles (less fill / drain / wave quantisation).
+  // CTA pairs (256 x BN tiles, tcgen05.mma.cta_group::2) unless NBEST_GEMM_CTA_GROUP=1 asks for the single-CTA kernel.
+  int CG = 2;
+  if (const char* cg = getenv("NBEST_GEMM_CTA_GROUP")) CG = atoi(cg) == 1 ? 1 : 2;
+  const int units = ctx->num_sms / CG;   // persistent work units: CTAs or CTA pairs
+  const int tile_m = BM * CG;
+  // BN = 256 halves the smem operand traffic per MMA. Pairs: always preferred (out-proj T x 768 x 768: 21 us vs 32 us
+  // with BN = 128). Single-CTA kernel: short-K problems with few tiles prefer BN = 128 (more, shorter tiles).
   int BN = (N % 256 == 0) ? 256 : 128;
-  if (BN == 256 && epilogue != NBEST_EPI_ACCUM_F32 && K <= 1024 &&
-      (int64_t)((M + BM - 1) / BM) * (N / 256) < 4LL * ctx->num_sms)
+  if (CG == 1 && BN == 256 && epilogue != NBEST_EPI_ACCUM_F32 && K <= 1024 &&
+      (int64_t)((M + tile_m - 1) / tile_m) * (N / 256) < 4LL * units)
     BN = 128;
   if (const char* force = getenv("NBEST_GEMM_BN")) {
     const int f = atoi(force);
@@ -414,15 +505,15 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
   g.M = M;
   g.N = N;
   g.K = K;
-  g.num_m_tiles = (M + BM - 1) / BM;
+  g.num_m_tiles = (M + tile_m - 1) / tile_m;
   g.num_n_tiles = N / BN;
   g.num_kb = (K + BK - 1) / BK;
   g.num_splits = 1;
   if (epilogue == NBEST_EPI_ACCUM_F32) {
-    // split the contraction so that (tiles x splits) fills ONE wave of SMs (measured best on B200: e.g. 72 tiles x 2,
-    // 54 x 2, 18 x 8 — a second wave or more splits only add fp32 atomic traffic), with >= 8 k-blocks per split
+    // split the contraction so that (tiles x splits) fills ONE wave of units (measured best on B200 — a second wave or
+    // more splits only add fp32 atomic traffic), with >= 8 k-blocks per split
     const int tiles = g.num_m_tiles * g.num_n_tiles;
-    int want = ctx->num_sms / tiles;
+    int want = units / tiles;
     int max_by_k = g.num_kb / 8 > 0 ? g.num_kb / 8 : 1;
     if (want > max_by_k) want = max_by_k;
     if (want < 1) want = 1;
@@ -433,7 +524,8 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
     g.num_splits = want;
   }
   g.debug = getenv("NBEST_GEMM_DEBUG") ? atoi(getenv("NBEST_GEMM_DEBUG")) : 0;
-  g.stages = (BN == 256) ? Cfg<256>::kStages : Cfg<128>::kStages;
+  g.stages = (CG == 2) ? ((BN == 256) ? Cfg<256, 2>::kStages : Cfg<128, 2>::kStages)
+                       : ((BN == 256) ? Cfg<256, 1>::kStages : Cfg<128, 1>::kStages);
   if (const char* st = getenv("NBEST_GEMM_STAGES")) {
     const int v = atoi(st);
     if (v >= 1 && v < g.stages) g.stages = v;
@@ -464,7 +556,7 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
     rc = nbest_make_tmap_bf16(ctx, &tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64);
   if (rc != NBEST_OK) return rc;
   if (!b_mn_major)
-    rc = nbest_make_tmap_bf16(ctx, &tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)BN);
+    rc = nbest_make_tmap_bf16(ctx, &tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)(BN / CG));
   else
     rc = nbest_make_tmap_bf16(ctx, &tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64);
   if (rc != NBEST_OK) return rc;
@@ -480,6 +572,10 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
     }
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (BN == 256) return dispatch<256>(ctx, a_mn_major, b_mn_major, epilogue, tmA, tmB, tmC, tmC2, g, s);
-  return dispatch<128>(ctx, a_mn_major, b_mn_major, epilogue, tmA, tmB, tmC, tmC2, g, s);
+  if (CG == 2) {
+    if (BN == 256) return dispatch<256, 2>(ctx, a_mn_major, b_mn_major, epilogue, tmA, tmB, tmC, tmC2, g, s);
+    return dispatch<128, 2>(ctx, a_mn_major, b_mn_major, epilogue, tmA, tmB, tmC, tmC2, g, s);
+  }
+  if (BN == 256) return dispatch<256, 1>(ctx, a_mn_major, b_mn_major, epilogue, tmA, tmB, tmC, tmC2, g, s);
+  return dispatch<128, 1>(ctx, a_mn_major, b_mn_major, epilogue, tmA, tmB, tmC, tmC2, g, s);
 }

@@ -68,6 +68,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
@@ -130,6 +131,63 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |
          (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- CTA pairs (cta_group::2): clusters of two CTAs
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `saddr` (a shared::cta address of this CTA's window) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// Relaxed: the arrive only orders tcgen05 traffic (handled by tcgen05.fence), no generic-proxy data is handed over; the
+// default .release.cluster form costs a MEMBAR.ALL + ERRBAR per arrive (12 % of the GELU GEMM's stall samples).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on an mbarrier that may live in the PEER CTA of the pair (bar_cluster_addr is
+// a shared::cluster address); the data lands in this CTA's shared memory.
+__device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* m, uint32_t bar_cluster_addr, void* smem_dst, int32_t c0,
+                                                int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cg2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs: 128 rows each] * B[smem of both CTAs: N/2 rows each]; issued by ONE
+// thread of the leader CTA (cluster rank 0) for the pair.
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on the mbarrier at this offset in EVERY CTA of cta_mask once all previously issued MMAs have completed.
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
 }
 
 // ---------------------------------------------------------------- legacy warp MMA (attention, short sequences)
@@ -202,8 +260,9 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// h = 0.5*(1 - erf(|z|/sqrt2)) and e = exp(-z^2/2), with xs = |z|*sqrt(log2(e)/2) so that e = 2^(-xs^2).
-__device__ __forceinline__ void gelu_tail(float z, float& h, float& e) {
+// w = h / e with h = 0.5*(1 - erf(|z|/sqrt2)) (the polynomial part of A&S 7.1.26) and e = exp(-z^2/2); xs = |z| *
+// sqrt(log2(e)/2) so that e = 2^(-xs^2).
+__device__ __forceinline__ void gelu_tail(float z, float& w, float& e) {
   const float xs = fabsf(z) * 0.8493218002880191f;
   const float t = rcp_approx(fmaf(0.2727374808792225f, xs, 1.0f));   // 1 / (1 + 0.3275911 |z|/sqrt2)
   e = ex2_approx(-xs * xs);
@@ -211,18 +270,21 @@ __device__ __forceinline__ void gelu_tail(float z, float& h, float& e) {
   poly = fmaf(poly, t, 0.5f * 1.421413741f);
   poly = fmaf(poly, t, 0.5f * -0.284496736f);
   poly = fmaf(poly, t, 0.5f * 0.254829592f);
-  h = poly * t * e;
+  w = poly * t;
 }
-__device__ __forceinline__ float gelu_fwd(float z) {   // z*Phi(z) = 0.5 z + |z| (0.5 - h)
-  float h, e;
-  gelu_tail(z, h, e);
-  return fmaf(fabsf(z), 0.5f - h, 0.5f * z);
+// z*Phi(z) with Phi = step(z) - sign(z) h:  relu(z) - |z| w e      (12 instructions, 2 MUFU)
+__device__ __forceinline__ float gelu_fwd(float z) {
+  float w, e;
+  gelu_tail(z, w, e);
+  return fmaf(-fabsf(z) * w, e, fmaxf(z, 0.f));
 }
-__device__ __forceinline__ float gelu_grad(float z) {  // Phi(z) + z phi(z)
-  float h, e;
-  gelu_tail(z, h, e);
-  const float Phi = 0.5f + copysignf(0.5f - h, z);
-  return fmaf(z * 0.39894228040143268f, e, Phi);
+// Phi(z) + z phi(z) = step(z) + sign(z) e (|z|/sqrt(2 pi) - w)
+__device__ __forceinline__ float gelu_grad(float z) {
+  float w, e;
+  gelu_tail(z, w, e);
+  const float d = fmaf(0.39894228040143268f, fabsf(z), -w);
+  const float ds = __uint_as_float(__float_as_uint(d) ^ (__float_as_uint(z) & 0x80000000u));   // sign(z) * d
+  return fmaf(ds, e, __float_as_int(z) >= 0 ? 1.0f : 0.f);   // step by SIGN BIT: +0 -> 1 - h(0) = 0.5, -0 -> 0 + h(0)
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -133,7 +133,8 @@ class TOD_ASR_Transformer_STC(nn.Module):
         self._step_seed = int(seed)
         # The head (and the MSE term) only ever read the [CLS] row of the last hidden state (reference models/model.py:
         # 46-47,58), so the last layer's attention output, out-projection, FFN and LayerNorms are computed for that row
-        # only; identical results, ~1/12 less encoder work. False = run the last layer on every token.
+        # only: ~1/12 less encoder work, identical results (with hidden dropout the compact rows draw a different, equally
+        # valid mask: mask indices follow the row layout). False = run the last layer on every token.
         self.cls_only_last_layer = True
         self._build_params(encoder_state, seed)
 

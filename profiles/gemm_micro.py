@@ -36,6 +36,10 @@ if __name__ == "__main__":
     uu = torch.randn(T2, 3072, device="cuda").to(torch.bfloat16)
     print("ffn2 dgrad dgelu       %8.1f us  %7.1f TFLOP/s" % bench(T2, 3072, 768, ops.EPI_DGELU, b_mn=True, aux=uu))
     print("ffn2 dgrad none        %8.1f us  %7.1f TFLOP/s" % bench(T2, 3072, 768, ops.EPI_NONE, b_mn=True))
+    r2 = torch.randn(T2, 768, device="cuda").to(torch.bfloat16)
+    print("ffn1 dgrad +res        %8.1f us  %7.1f TFLOP/s" % bench(T2, 768, 3072, ops.EPI_ADD, b_mn=True, aux=r2))
+    print("outproj dgrad          %8.1f us  %7.1f TFLOP/s" % bench(T2, 768, 768, ops.EPI_NONE, b_mn=True))
+    print("qkv dgrad +res         %8.1f us  %7.1f TFLOP/s" % bench(T2, 768, 2304, ops.EPI_ADD, b_mn=True, aux=r2))
     r = torch.randn(T, 768, device="cuda").to(torch.bfloat16)
     b768 = torch.randn(768, device="cuda")
     print("outproj bias+drop+res  %8.1f us  %7.1f TFLOP/s" % bench(T, 768, 768, ops.EPI_BIAS_DROP_RES, bias=b768, aux=r, p_drop=0.1, seed=1))

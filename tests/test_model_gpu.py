@@ -248,7 +248,9 @@ def test_dropout_training_step_is_finite_and_seeded():
 @pytest.mark.parametrize("l2", [True, False])
 def test_cls_only_last_layer_equals_full_last_layer(l2):
     """The last encoder layer's post-attention block runs on the [CLS] rows only (reference models/model.py:46-47,58 drop
-    every other row). With the same seeds (dropout ON) it must give the scores, losses and gradients of the full path."""
+    every other row). With attention and head dropout ON (their mask indices do not depend on the row layout) it must
+    give the scores, losses and gradients of the full path; the hidden dropout of the last layer indexes its mask by the
+    row of the tensor it is applied to, so the compact path draws a different, equally valid mask there (hence p = 0)."""
     from oracle import stc_oracle as O
     from nbest_b200.synth import synth_batch
     hier_o, hj = _hier()
@@ -258,7 +260,7 @@ def test_cls_only_last_layer_equals_full_last_layer(l2):
     d = lambda k: batch[k].cuda()
     res = []
     for compact in (True, False):
-        model = _build(cfg, hier_o, hj, params, dropout=0.3, hidden_dropout=0.1, attn_dropout=0.1)
+        model = _build(cfg, hier_o, hj, params, dropout=0.3, hidden_dropout=0.0, attn_dropout=0.1)
         model.cls_only_last_layer = compact
         model.train()
         model.zero_grad()
