@@ -106,8 +106,8 @@ __device__ __forceinline__ void zero_acc(float (&a)[8][4]) {
     for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
 }
 
-// dropout index of attention probability (head h, query token tq (global), key j inside the sequence)
-__device__ __forceinline__ uint32_t pidx(int h, int T, int tq, int j) { return ((uint32_t)h * (uint32_t)T + (uint32_t)tq) * 512u + (uint32_t)j; }
+// Dropout of the attention probabilities: ptx.cuh attn_quad / attn_lane map (head, query token, key) to a hash counter
+// and a 16-bit lane such that one hash serves the four elements a thread holds per 16-key group.
 
 // One CTA walks HPC heads of one (sequence, 64-row block): the tiles of iteration i+1 (next key block or next head)
 // are prefetched with cp.async into the other shared-memory stage while iteration i is computed, so the global-load
@@ -222,16 +222,17 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict
     }
     if (thr) {
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+      for (int np = 0; np < 4; ++np)
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          if (nt >= 2 * npairs) continue;
+          if (np >= npairs) continue;
           const int tq = s0 + q0 + warp * 16 + (lane >> 2) + 8 * r;
-          const int j = k0 + nt * 8 + (lane & 3) * 2;
-          bool keep0, keep1;
-          dropout_keep2(seed, pidx(h, T, tq, j), thr, keep0, keep1);
-          s[nt][2 * r] = keep0 ? s[nt][2 * r] * rscale : 0.f;
-          s[nt][2 * r + 1] = keep1 ? s[nt][2 * r + 1] * rscale : 0.f;
+          // keys k0 + 16 np + 2 (lane & 3) + {0, 1, 8, 9}: one quad
+          const uint2 hh = dropout_quad(seed, attn_quad_row(h, T, tq) + (uint32_t)(((k0 >> 4) + np) << 2) + (lane & 3));
+          s[2 * np][2 * r] = (hh.x & 0xFFFFu) >= thr ? s[2 * np][2 * r] * rscale : 0.f;
+          s[2 * np][2 * r + 1] = (hh.x >> 16) >= thr ? s[2 * np][2 * r + 1] * rscale : 0.f;
+          s[2 * np + 1][2 * r] = (hh.y & 0xFFFFu) >= thr ? s[2 * np + 1][2 * r] * rscale : 0.f;
+          s[2 * np + 1][2 * r + 1] = (hh.y >> 16) >= thr ? s[2 * np + 1][2 * r + 1] * rscale : 0.f;
         }
     }
     mma_p_b_kn(o, s, uV, lane, npairs);
@@ -351,22 +352,28 @@ attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __res
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int eb = 0; eb < 2; ++eb) {
         if (nt >= 2 * npq) continue;
-        const int qc = nt * 8 + (lane & 3) * 2 + (e & 1);
-        const int r = e >> 1;
-        const float p = kval[r] ? ex2_approx(st_[nt][e] * sl2 - sm.lse[st][qc]) : 0.f;
-        float dp = dpt[nt][e];
-        float pd = p;
-        if (thr) {
-          const int tq = s0 + q0 + qc;
-          const int j = k0 + warp * 16 + (lane >> 2) + 8 * r;
-          const bool keep = dropout_keep(seed, pidx(h, T, tq, j), thr);
-          pd = keep ? p * rscale : 0.f;
-          dp = keep ? dp * rscale : 0.f;
+        const int qc = nt * 8 + (lane & 3) * 2 + eb;
+        // this thread's two keys of query qc (k0 + 16 warp + lane/4 + {0, 8}) are lanes (l, l + 2) of ONE quad
+        uint2 hh = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+        if (thr) hh = dropout_quad(seed, attn_quad_row(h, T, s0 + q0 + qc) + (uint32_t)(((k0 >> 4) + warp) << 2) + (lane >> 3));
+        const float lse_q = sm.lse[st][qc], delta_q = sm.delta[st][qc];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int e = 2 * r + eb;
+          const float p = kval[r] ? ex2_approx(st_[nt][e] * sl2 - lse_q) : 0.f;
+          float dp = dpt[nt][e];
+          float pd = p;
+          if (thr) {
+            const uint32_t w = r ? hh.y : hh.x;
+            const bool keep = (((lane >> 2) & 1) ? (w >> 16) : (w & 0xFFFFu)) >= thr;
+            pd = keep ? p * rscale : 0.f;
+            dp = keep ? dp * rscale : 0.f;
+          }
+          st_[nt][e] = pd;                                   // dropped P^T  -> dV
+          dpt[nt][e] = p * (dp - delta_q);                   // dS^T         -> dK
         }
-        st_[nt][e] = pd;                                   // dropped P^T  -> dV
-        dpt[nt][e] = p * (dp - sm.delta[st][qc]);          // dS^T         -> dK
       }
     mma_p_b_kn(dv, st_, uO, lane, npq);   // dV += P^T dO   (B = dO [q][d])
     mma_p_b_kn(dk, dpt, uQ, lane, npq);   // dK += dS^T Q   (B = Q  [q][d])
@@ -468,19 +475,27 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restr
     mma_a_tile_b_nk(s, uQ, warp * 16, uK, lane, npk);     // S  [16 q x 64 keys]
     mma_a_tile_b_nk(dp, uO, warp * 16, uV, lane, npk);    // dP [16 q x 64 keys] = dO V^T
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int np = 0; np < 4; ++np)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (nt >= 2 * npk) continue;
-        const int kc = nt * 8 + (lane & 3) * 2 + (e & 1);
-        const int r = e >> 1;
-        const float p = sm.valid[st][kc] ? ex2_approx(s[nt][e] * sl2 - lse2[r]) : 0.f;
-        float d = dp[nt][e];
+      for (int r = 0; r < 2; ++r) {
+        if (np >= npk) continue;
+        uint2 hh = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
         if (thr) {
           const int tq = s0 + q0 + warp * 16 + (lane >> 2) + 8 * r;
-          d = dropout_keep(seed, pidx(h, T, tq, k0 + kc), thr) ? d * rscale : 0.f;
+          hh = dropout_quad(seed, attn_quad_row(h, T, tq) + (uint32_t)(((k0 >> 4) + np) << 2) + (lane & 3));
         }
-        s[nt][e] = p * (d - dl[r]);                   // dS
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                   // keys 16 np + 2 (lane & 3) + {0, 1, 8, 9}
+          const int nt = 2 * np + (i >> 1), e = 2 * r + (i & 1);
+          const int kc = nt * 8 + (lane & 3) * 2 + (i & 1);
+          const float p = sm.valid[st][kc] ? ex2_approx(s[nt][e] * sl2 - lse2[r]) : 0.f;
+          float d = dp[nt][e];
+          if (thr) {
+            const uint32_t w = (i & 2) ? hh.y : hh.x;
+            d = ((i & 1) ? (w >> 16) : (w & 0xFFFFu)) >= thr ? d * rscale : 0.f;
+          }
+          s[nt][e] = p * (d - dl[r]);                   // dS
+        }
       }
     mma_p_b_kn(dq, s, uK, lane, npk);                 // dQ += dS K   (B = K [key][d])
     }   // warp_active

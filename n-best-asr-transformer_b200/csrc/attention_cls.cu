@@ -21,7 +21,6 @@ constexpr int kWarps = 4;
 constexpr int kMaxLen = 512;
 constexpr float kLog2e = 1.4426950408889634f;
 
-__device__ __forceinline__ uint32_t pidx(int h, int T, int tq, int j) { return ((uint32_t)h * (uint32_t)T + (uint32_t)tq) * 512u + (uint32_t)j; }
 
 __device__ __forceinline__ void load_row64(const __nv_bfloat16* p, float (&v)[D]) {
 #pragma unroll
@@ -94,7 +93,7 @@ attn_cls_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __rest
   const float inv = sum > 0.f ? 1.0f / sum : 0.f;
   for (int j = lane; j < L; j += 32) {
     float p = sp[warp][j] * inv;
-    if (thr) p = dropout_keep(seed, pidx(h, T, s0, j), thr) ? p * rscale : 0.f;
+    if (thr) p = attn_dropout_keep(seed, h, T, s0, j, thr) ? p * rscale : 0.f;
     sp[warp][j] = p;
   }
   __syncwarp();
@@ -142,7 +141,7 @@ attn_cls_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __rest
     float dp = dot_row64(qkv + (int64_t)(s0 + j) * ld + 2 * hd + h * D, dO);
     float pd = p;
     if (thr) {
-      const bool keep = dropout_keep(seed, pidx(h, T, s0, j), thr);
+      const bool keep = attn_dropout_keep(seed, h, T, s0, j, thr);
       pd = keep ? p * rscale : 0.f;
       dp = keep ? dp * rscale : 0.f;
     }

@@ -130,10 +130,12 @@ __device__ __forceinline__ void ln_apply_store(const float4 (&x)[VPL], RowStats 
     y.z = (x[i].z - st.mean) * st.rstd * g.z + b.z;
     y.w = (x[i].w - st.mean) * st.rstd * g.w + b.w;
     if (thr) {
-      y.x = dropout_keep(seed, row_base + c + 0, thr) ? y.x * scale : 0.f;
-      y.y = dropout_keep(seed, row_base + c + 1, thr) ? y.y * scale : 0.f;
-      y.z = dropout_keep(seed, row_base + c + 2, thr) ? y.z * scale : 0.f;
-      y.w = dropout_keep(seed, row_base + c + 3, thr) ? y.w * scale : 0.f;
+      bool k0_, k1_, k2_, k3_;
+      dropout_keep4(seed, row_base + c, thr, k0_, k1_, k2_, k3_);
+      y.x = k0_ ? y.x * scale : 0.f;
+      y.y = k1_ ? y.y * scale : 0.f;
+      y.z = k2_ ? y.z * scale : 0.f;
+      y.w = k3_ ? y.w * scale : 0.f;
     }
     *reinterpret_cast<uint2*>(yrow + c) = f4_to_bf16x4(y);
   }
@@ -298,10 +300,12 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dyin, const __nv_bfloat16* __res
       float4 m = dy[i];
       if (dxm != nullptr) {
         const uint32_t base = (uint32_t)t * H + c;
-        m.x = dropout_keep(seed, base + 0, thr) ? m.x * scale : 0.f;
-        m.y = dropout_keep(seed, base + 1, thr) ? m.y * scale : 0.f;
-        m.z = dropout_keep(seed, base + 2, thr) ? m.z * scale : 0.f;
-        m.w = dropout_keep(seed, base + 3, thr) ? m.w * scale : 0.f;
+        bool k0_, k1_, k2_, k3_;
+        dropout_keep4(seed, base, thr, k0_, k1_, k2_, k3_);
+        m.x = k0_ ? m.x * scale : 0.f;
+        m.y = k1_ ? m.y * scale : 0.f;
+        m.z = k2_ ? m.z * scale : 0.f;
+        m.w = k3_ ? m.w * scale : 0.f;
         *reinterpret_cast<uint2*>(dxm + (int64_t)t * H + c) = f4_to_bf16x4(m);
       }
       f4_acc(dbia[i], m);
@@ -343,10 +347,12 @@ embed_ln_bwd_kernel(const int32_t* __restrict__ tokens, const uint8_t* __restric
       dy[i] = bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(dyin + (int64_t)t * H + c)));
       if (thr) {
         const uint32_t base = (uint32_t)t * H + c;
-        dy[i].x = dropout_keep(seed, base + 0, thr) ? dy[i].x * scale : 0.f;
-        dy[i].y = dropout_keep(seed, base + 1, thr) ? dy[i].y * scale : 0.f;
-        dy[i].z = dropout_keep(seed, base + 2, thr) ? dy[i].z * scale : 0.f;
-        dy[i].w = dropout_keep(seed, base + 3, thr) ? dy[i].w * scale : 0.f;
+        bool k0_, k1_, k2_, k3_;
+        dropout_keep4(seed, base, thr, k0_, k1_, k2_, k3_);
+        dy[i].x = k0_ ? dy[i].x * scale : 0.f;
+        dy[i].y = k1_ ? dy[i].y * scale : 0.f;
+        dy[i].z = k2_ ? dy[i].z * scale : 0.f;
+        dy[i].w = k3_ ? dy[i].w * scale : 0.f;
       }
     }
     ln_bwd_row(xhat, dy, rs, gamma, lane, dgam, dbet);

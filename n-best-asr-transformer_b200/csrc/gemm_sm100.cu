@@ -336,11 +336,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (g.drop_thresh != 0) {
                   const uint32_t base = (uint32_t)row * (uint32_t)g.N + (uint32_t)nc;
 #pragma unroll
-                  for (int j = 0; j < 32; j += 2) {
-                    bool k0, k1;
-                    dropout_keep2(g.seed, base + j, g.drop_thresh, k0, k1);   // base is even (N and nc are even)
+                  for (int j = 0; j < 32; j += 4) {
+                    bool k0, k1, k2, k3;
+                    dropout_keep4(g.seed, base + j, g.drop_thresh, k0, k1, k2, k3);   // base % 4 == 0 (N, nc multiples of 32)
                     v[j] = k0 ? v[j] * g.drop_scale : 0.f;
                     v[j + 1] = k1 ? v[j + 1] * g.drop_scale : 0.f;
+                    v[j + 2] = k2 ? v[j + 2] * g.drop_scale : 0.f;
+                    v[j + 3] = k3 ? v[j + 3] * g.drop_scale : 0.f;
                   }
                 }
 #pragma unroll

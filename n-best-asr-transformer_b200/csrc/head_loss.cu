@@ -61,10 +61,12 @@ stc_head_fwd_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restri
       float4 fv = *reinterpret_cast<const float4*>(f + d);
       if (thr) {
         const uint32_t base = ((uint32_t)g * (uint32_t)B + (uint32_t)b) * H + d;
-        fv.x = dropout_keep(seed, base + 0, thr) ? fv.x * rscale : 0.f;
-        fv.y = dropout_keep(seed, base + 1, thr) ? fv.y * rscale : 0.f;
-        fv.z = dropout_keep(seed, base + 2, thr) ? fv.z * rscale : 0.f;
-        fv.w = dropout_keep(seed, base + 3, thr) ? fv.w * rscale : 0.f;
+        bool k0_, k1_, k2_, k3_;
+        dropout_keep4(seed, base, thr, k0_, k1_, k2_, k3_);
+        fv.x = k0_ ? fv.x * rscale : 0.f;
+        fv.y = k1_ ? fv.y * rscale : 0.f;
+        fv.z = k2_ ? fv.z * rscale : 0.f;
+        fv.w = k3_ ? fv.w * rscale : 0.f;
       }
       acc += wv.x * fv.x + wv.y * fv.y + wv.z * fv.z + wv.w * fv.w;
     }

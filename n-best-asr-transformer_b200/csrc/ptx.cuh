@@ -225,27 +225,46 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
-// Counter-based dropout RNG: one murmur3-finalised 32-bit hash per PAIR of consecutive elements, 16 bits each.
-// thr16 = round(p_drop * 65536); keep iff the element's 16-bit lane >= thr16. Forward and backward regenerate the
-// same mask from (seed, element index); every kernel addresses pairs (2j, 2j+1) from one thread, so the hash is shared.
-__device__ __forceinline__ uint32_t dropout_hash(uint32_t seed, uint32_t pair_idx) {
-  uint32_t h = pair_idx * 0x9E3779B1u + seed;
-  h ^= h >> 16;
-  h *= 0x85EBCA6Bu;
-  h ^= h >> 13;
-  h *= 0xC2B2AE35u;
-  h ^= h >> 16;
-  return h;
+// Counter-based dropout RNG: ONE hash yields the keep/drop decisions of a QUAD of elements (4 x 16-bit lanes).
+//   x = fold(q * C1) ^ seed;  x ^= x >> 16;  (a, b) = (fold(x * C2), fold(x * C3)),  fold(m) = lo32(m) ^ hi32(m)
+// i.e. three 32x32->64 multiplies and four logic ops per four elements (the murmur3 finaliser it replaces cost 9
+// instructions per PAIR and was the largest single item of the attention kernels' instruction mix). The host passes
+// avalanche-mixed seeds (ops._seed), so per-(step, layer, site) streams are unrelated. Checked on the host restatement
+// (tests/test_abi_and_host.py): uniform lanes, no lane / stride / cross-seed correlation, geometric gaps.
+// thr16 = round(p_drop * 65536); element kept iff its 16-bit lane >= thr16. Forward and backward regenerate the same
+// mask from (seed, element index).
+__device__ __forceinline__ uint32_t fold64(uint64_t m) { return static_cast<uint32_t>(m) ^ static_cast<uint32_t>(m >> 32); }
+__device__ __forceinline__ uint2 dropout_quad(uint32_t seed, uint32_t quad_idx) {
+  uint32_t x = fold64(static_cast<uint64_t>(quad_idx) * 0x9E3779B1u) ^ seed;
+  x ^= x >> 16;
+  return make_uint2(fold64(static_cast<uint64_t>(x) * 0x85EBCA6Bu), fold64(static_cast<uint64_t>(x) * 0xC2B2AE35u));
 }
-// idx_even must be even: decisions for elements idx_even and idx_even + 1.
-__device__ __forceinline__ void dropout_keep2(uint32_t seed, uint32_t idx_even, uint32_t thr16, bool& k0, bool& k1) {
-  const uint32_t h = dropout_hash(seed, idx_even >> 1);
-  k0 = (h & 0xFFFFu) >= thr16;
-  k1 = (h >> 16) >= thr16;
+__device__ __forceinline__ uint32_t quad_lane(uint2 h, uint32_t lane) {   // lane in [0, 4)
+  const uint32_t w = (lane & 2u) ? h.y : h.x;
+  return (lane & 1u) ? (w >> 16) : (w & 0xFFFFu);
+}
+// elements idx4 .. idx4 + 3 (idx4 a multiple of 4)
+__device__ __forceinline__ void dropout_keep4(uint32_t seed, uint32_t idx4, uint32_t thr16, bool& k0, bool& k1, bool& k2,
+                                              bool& k3) {
+  const uint2 h = dropout_quad(seed, idx4 >> 2);
+  k0 = (h.x & 0xFFFFu) >= thr16;
+  k1 = (h.x >> 16) >= thr16;
+  k2 = (h.y & 0xFFFFu) >= thr16;
+  k3 = (h.y >> 16) >= thr16;
 }
 __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t idx, uint32_t thr16) {
-  const uint32_t h = dropout_hash(seed, idx >> 1);
-  return ((idx & 1u) ? (h >> 16) : (h & 0xFFFFu)) >= thr16;
+  return quad_lane(dropout_quad(seed, idx >> 2), idx & 3u) >= thr16;
+}
+// Attention probabilities: element (head h, global query token tq, key j inside the sequence, j < 512). The quad of a
+// key is chosen so that the four accumulator elements an mma.sync thread holds in one 16-key group (keys c, c+1, c+8,
+// c+9 of a query row) share ONE hash, and so do the two keys (j, j+8) a thread of the S^T formulation holds per query.
+__device__ __forceinline__ uint32_t attn_quad_row(int h, int T, int tq) { return ((uint32_t)h * (uint32_t)T + (uint32_t)tq) * 128u; }
+__device__ __forceinline__ uint32_t attn_quad(int h, int T, int tq, int j) {
+  return attn_quad_row(h, T, tq) + (((uint32_t)j >> 4) << 2) + (((uint32_t)j & 7u) >> 1);
+}
+__device__ __forceinline__ uint32_t attn_lane(int j) { return ((uint32_t)j & 1u) | (((uint32_t)j >> 2) & 2u); }
+__device__ __forceinline__ bool attn_dropout_keep(uint32_t seed, int h, int T, int tq, int j, uint32_t thr16) {
+  return quad_lane(dropout_quad(seed, attn_quad(h, T, tq, j)), attn_lane(j)) >= thr16;
 }
 
 // erf-based GELU pieces. Phi(z) = 0.5*(1+erf(z/sqrt2)) via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7 + approx-rcp/ex2

@@ -123,13 +123,21 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, epilogue=EPI_NONE, bias=No
         rc = _lib.lib().nbest_gemm_bf16(
             ctx.handle, _p(a), a.stride(0), int(a_mn_major), _p(b), b.stride(0), int(b_mn_major), _p(out), out.stride(0),
             M, N, K, int(epilogue), _p(bias), _p(aux), aux.stride(0) if aux is not None else 0, _p(out2), float(p_drop),
-            int(seed) & 0xFFFFFFFF, _stream())
+            _seed(seed), _stream())
     ctx.check(rc)
     return out
 
 
 def _seed(s):
-    return int(s) & 0xFFFFFFFF
+    """32-bit seed handed to the kernels, avalanche-mixed (murmur3 finaliser): callers pass small structured values
+    (step * 1000003 + layer * 16 + site) and the device-side quad hash xors the seed in after its first multiply."""
+    s = int(s) & 0xFFFFFFFF
+    s ^= s >> 16
+    s = (s * 0x85EBCA6B) & 0xFFFFFFFF
+    s ^= s >> 13
+    s = (s * 0xC2B2AE35) & 0xFFFFFFFF
+    s ^= s >> 16
+    return s
 
 
 # ---------------------------------------------------------------------------------------------------------- packing

@@ -410,3 +410,55 @@ def train_step(params, cfg, hier, batch, opt_state, hp, drop=None):
             bertadam_step(params, grads, opt_state, hp["lr"], hp["bert_lr"], hp["warmup"], hp["t_total"])
     return (dict(total=float(total.detach()), **{k: float(v.detach()) for k, v in terms.items()}), grads,
             (top, bottoms, final, asr, trans))
+
+
+# ----------------------------------------------------------------------------------------------- dropout mask restatement
+# The reference draws its dropout masks from torch's Philox stream (nn.Dropout inside HF BERT, hierarchical_classifier.py:
+# 41,46); any independent Bernoulli(1-p) mask is an equally valid realisation, so the CUDA path uses its own counter-based
+# hash (csrc/ptx.cuh dropout_quad) that forward and backward can both regenerate. This numpy restatement pins it bit-exactly.
+def mix_seed(s):
+    """ops._seed: murmur3 finaliser applied on the host to the structured (step, layer, site) seed."""
+    s = int(s) & 0xFFFFFFFF
+    s ^= s >> 16
+    s = (s * 0x85EBCA6B) & 0xFFFFFFFF
+    s ^= s >> 13
+    s = (s * 0xC2B2AE35) & 0xFFFFFFFF
+    s ^= s >> 16
+    return s
+
+
+def dropout_lanes(seed, quad_idx):
+    """csrc/ptx.cuh dropout_quad: four 16-bit lanes per 32-bit counter. `seed` is the MIXED seed; returns int64 [..., 4]."""
+    import numpy as np
+    m32 = np.uint64(0xFFFFFFFF)
+    fold = lambda m: ((m & m32) ^ (m >> np.uint64(32))) & m32
+    q = np.asarray(quad_idx).astype(np.uint64) & m32
+    x = (fold(q * np.uint64(0x9E3779B1)) ^ np.uint64(seed)) & m32
+    x ^= x >> np.uint64(16)
+    a, b = fold(x * np.uint64(0x85EBCA6B)), fold(x * np.uint64(0xC2B2AE35))
+    s16, m16 = np.uint64(16), np.uint64(0xFFFF)
+    return np.stack([a & m16, a >> s16, b & m16, b >> s16], -1).astype(np.int64)
+
+
+def dropout_threshold(p):
+    t = p * 65536.0 + 0.5
+    return 0 if p <= 0 else (65535 if t >= 65535.0 else int(t))
+
+
+def dropout_keep_mask(seed, n, p):
+    """Keep mask of elements 0 .. n-1 of a row-major tensor (element e = lane e % 4 of quad e // 4); seed un-mixed."""
+    import numpy as np
+    lanes = dropout_lanes(mix_seed(seed), np.arange((n + 3) // 4)).reshape(-1)[:n]
+    return lanes >= dropout_threshold(p)
+
+
+def attn_dropout_keep_mask(seed, heads, T, tq, L, p):
+    """Keep mask [heads, L] of the attention probabilities of global query token tq over the L keys of its sequence
+    (csrc/ptx.cuh attn_quad / attn_lane)."""
+    import numpy as np
+    j = np.arange(L)
+    h = np.arange(heads)[:, None]
+    quad = ((h * T + tq) * 128 + ((j >> 4) << 2) + ((j & 7) >> 1))[..., None]
+    lane = ((j & 1) | ((j >> 2) & 2))[None, :, None]
+    lanes = dropout_lanes(mix_seed(seed), quad[..., 0])
+    return np.take_along_axis(lanes, np.broadcast_to(lane, lanes.shape[:2] + (1,)), -1)[..., 0] >= dropout_threshold(p)

@@ -138,3 +138,35 @@ def test_hierarchy_tables_are_consistent():
     assert sum(hier.none_col) == 10                                          # one NONE value per multi-way group
     for g in range(hier.n_groups):
         assert hier.none_col[hier.grp_off[g + 1] - 1] == 1                   # ... and it is the group's last column
+
+
+def test_dropout_hash_restatement_is_a_sound_bernoulli_source():
+    """The counter-based dropout hash (csrc/ptx.cuh dropout_quad, restated in oracle.stc_oracle.dropout_lanes): uniform
+    16-bit lanes, drop rate = p, no correlation between lanes / neighbours / the strides the kernels use, unrelated streams
+    for neighbouring seeds, geometric gaps between drops."""
+    import numpy as np
+    from oracle import stc_oracle as O
+    n_q = 1 << 20
+    q = np.arange(n_q)
+    for p in (0.1, 0.3):
+        thr = O.dropout_threshold(p)
+        for raw_seed in (1, 2, 5 * 1000003 + 3 * 16 + 2):
+            lanes = O.dropout_lanes(O.mix_seed(raw_seed), q)
+            drop = lanes < thr
+            assert np.all(np.abs(drop.mean(0) - p) < 4 * np.sqrt(p * (1 - p) / n_q))
+            for i in range(4):      # chi-square on 256 bins, 255 dof: mean 255, sd 22.6
+                h = np.bincount(lanes[:, i] >> 8, minlength=256)
+                assert ((h - n_q / 256) ** 2 / (n_q / 256)).sum() < 255 + 6 * 22.6
+            d = drop.astype(np.float64) - p
+            corr = lambda a, b: abs(float((a * b).mean())) / (p * (1 - p))
+            for i in range(4):
+                for k in range(i + 1, 4):
+                    assert corr(d[:, i], d[:, k]) < 5e-3
+            flat = d.reshape(-1)
+            for s in (1, 2, 3, 4, 8, 16, 64, 128, 512, 768, 3072, 65536):
+                assert corr(flat[:-s], flat[s:]) < 5e-3, s
+    a = (O.dropout_lanes(O.mix_seed(7), q) < 6554).astype(float) - 0.1
+    b = (O.dropout_lanes(O.mix_seed(8), q) < 6554).astype(float) - 0.1
+    assert abs(float((a * b).mean())) / 0.09 < 5e-3
+    gaps = np.diff(np.nonzero(O.dropout_keep_mask(3, 1 << 21, 0.1) == 0)[0])
+    assert abs(gaps.mean() - 10.0) < 0.1 and abs(gaps.var() - 90.0) < 3.0
