@@ -4,6 +4,8 @@
 //
 // Reference counterparts: utils/bert_xlnet_inputs.py:91-102 + models/model.py:43 (packing / key mask),
 // transformers modeling_bert.py:102-112 (BertEmbeddings), :294-298 and :352-356 (residual LayerNorms).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -170,22 +172,80 @@ embed_ln_fwd_kernel(const int32_t* __restrict__ tokens, const uint8_t* __restric
   ln_apply_store(x, st, gamma, beta, y + (int64_t)t * H, lane, thr, scale, seed, (uint32_t)t * H);
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// ---- 16-byte row chunks: lane owns columns 8 (lane + 32 i) + k, i < 3, k < 8 (a 768-wide bf16 row = 96 chunks) ----
+constexpr int CPL = H / 256;   // 16-byte chunks per lane (3)
+
+__device__ __forceinline__ void unpack8(const uint4 u, float (&v)[8]) {
+  v[0] = bf16lo(u.x);
+  v[1] = bf16hi(u.x);
+  v[2] = bf16lo(u.y);
+  v[3] = bf16hi(u.y);
+  v[4] = bf16lo(u.z);
+  v[5] = bf16hi(u.z);
+  v[6] = bf16lo(u.w);
+  v[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void load8f(const float* __restrict__ p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// Residual LayerNorm forward. Each warp normalises kRowsPerWarp rows whose 16-byte loads are all issued up front (the
+// kernel is pure streaming: memory-level parallelism per warp is what sets its bandwidth).
+template <int kLnFwdRows>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, kLnFwdRows <= 2 ? 4 : 2)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ xin, const float* __restrict__ gamma, const float* __restrict__ beta,
               float eps, int T, __nv_bfloat16* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
-  const int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (t >= T) return;
   const int lane = threadIdx.x & 31;
-  const __nv_bfloat16* xr = xin + (int64_t)t * H;
-  float4 x[VPL];
+  const int t0 = (blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * kLnFwdRows;
+  if (t0 >= T) return;
+  uint4 raw[kLnFwdRows][CPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) x[i] = bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(xr + 4 * (lane + 32 * i))));
-  const RowStats st = row_stats(x, eps);
-  if (lane == 0) {
-    if (mean) mean[t] = st.mean;
-    if (rstd) rstd[t] = st.rstd;
+  for (int r = 0; r < kLnFwdRows; ++r) {
+    const int t = min(t0 + r, T - 1);
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) raw[r][i] = __ldg(reinterpret_cast<const uint4*>(xin + (int64_t)t * H) + lane + 32 * i);
   }
-  ln_apply_store(x, st, gamma, beta, y + (int64_t)t * H, lane, 0u, 1.f, 0u, 0u);
+#pragma unroll
+  for (int r = 0; r < kLnFwdRows; ++r) {
+    const int t = t0 + r;
+    if (t >= T) break;
+    float x[CPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      unpack8(raw[r][i], x[i]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += x[i][k];
+    }
+    const float mu = warp_sum(s) * (1.0f / H);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = x[i][k] - mu;
+        q = fmaf(d, d, q);
+      }
+    const float rs = rsqrtf(warp_sum(q) * (1.0f / H) + eps);
+    if (lane == 0) {
+      if (mean) mean[t] = mu;
+      if (rstd) rstd[t] = rs;
+    }
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const int c = 8 * (lane + 32 * i);
+      float g[8], b[8], o[8];
+      load8f(gamma + c, g);
+      load8f(beta + c, b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaf((x[i][k] - mu) * rs, g[k], b[k]);
+      *(reinterpret_cast<uint4*>(y + (int64_t)t * H) + lane + 32 * i) = pack8(o);
+    }
+  }
 }
 
 // Block-level reduction of per-warp column partials (VPL float4 per lane) followed by one atomic per column per block.
@@ -246,74 +306,137 @@ __device__ __forceinline__ void ln_bwd_row(const float4 (&xhat)[VPL], float4 (&d
   }
 }
 
+// Residual LayerNorm backward (+ the dropout-masked gradient and the bias gradient of the dense layer before it).
+// Persistent, one block (8 warps) per SM: every lane carries 72 column accumulators (dgamma, dbeta, dbias), so occupancy
+// cannot supply memory-level parallelism; instead each warp streams its rows through a private 4-deep cp.async ring in
+// shared memory (x row + dy row = 3 KiB per stage, 96 KiB per block): three tokens are always in flight per warp. A lane
+// reads back exactly the chunks it copied, so the ring needs no cross-lane synchronisation at all.
+constexpr int kLnStages = 4;
+constexpr int kLnStageBytes = 2 * H * 2;                                   // x row + dy row
+constexpr int kLnBwdSmem = kWarpsPerBlock * kLnStages * kLnStageBytes;     // 96 KiB (>= the 24 KiB the final reduce needs)
+
+__device__ __forceinline__ void block_reduce_cols8_atomic(const float (&acc)[CPL][8], float* __restrict__ out, float* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    float* dst = sh + warp * H + 8 * (lane + 32 * i);
+    *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+  }
+  __syncthreads();
+  for (int c = 4 * threadIdx.x; c < H; c += 4 * blockDim.x) {
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; ++w) {
+      const float4 v = *reinterpret_cast<const float4*>(sh + w * H + c);
+      s4.x += v.x;
+      s4.y += v.y;
+      s4.z += v.z;
+      s4.w += v.w;
+    }
+    red_add_v4(out + c, s4);
+  }
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dyin, const __nv_bfloat16* __restrict__ xin, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, int T, __nv_bfloat16* __restrict__ dx,
               __nv_bfloat16* __restrict__ dxm, uint32_t thr, float scale, uint32_t seed, float* __restrict__ dgamma,
               float* __restrict__ dbeta, float* __restrict__ dbias) {
-  __shared__ float sh[kWarpsPerBlock * H];
+  extern __shared__ __align__(16) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 dgam[VPL], dbet[VPL], dbia[VPL];
+  const uint32_t ring = smem_u32(ln_smem) + warp * (kLnStages * kLnStageBytes);
+  float dgam[CPL][8], dbet[CPL][8], dbia[CPL][8], gam[CPL][8];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) dgam[i] = dbet[i] = dbia[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  // software pipeline: the packed bf16 rows of the warp's NEXT token are in flight while the current one is reduced
-  // (the kernel runs at one block per SM because of its 72 column accumulators per lane, so memory-level parallelism
-  // has to come from inside the warp)
-  const int tstep = gridDim.x * kWarpsPerBlock;
-  int t = blockIdx.x * kWarpsPerBlock + warp;
-  uint2 nx[VPL], ndy[VPL];
-  float nmu = 0.f, nrs = 0.f;
-  if (t < T) {
+  for (int i = 0; i < CPL; ++i) {
+    load8f(gamma + 8 * (lane + 32 * i), gam[i]);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int c = 4 * (lane + 32 * i);
-      nx[i] = __ldg(reinterpret_cast<const uint2*>(xin + (int64_t)t * H + c));
-      ndy[i] = __ldg(reinterpret_cast<const uint2*>(dyin + (int64_t)t * H + c));
-    }
-    nmu = mean[t];
-    nrs = rstd[t];
+    for (int k = 0; k < 8; ++k) dgam[i][k] = dbet[i][k] = dbia[i][k] = 0.f;
   }
-  for (; t < T; t += tstep) {
-    const float mu = nmu, rs = nrs;
-    float4 xhat[VPL], dy[VPL];
+  const int tstep = gridDim.x * kWarpsPerBlock;
+  const int t0 = blockIdx.x * kWarpsPerBlock + warp;
+  auto issue = [&](int t, int stage) {
+    if (t < T) {
+      const uint32_t dst = ring + stage * kLnStageBytes + lane * 16;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const float4 xv = bf16x4_to_f4(nx[i]);
-      xhat[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-      dy[i] = bf16x4_to_f4(ndy[i]);
-    }
-    if (t + tstep < T) {
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        const int c = 4 * (lane + 32 * i);
-        nx[i] = __ldg(reinterpret_cast<const uint2*>(xin + (int64_t)(t + tstep) * H + c));
-        ndy[i] = __ldg(reinterpret_cast<const uint2*>(dyin + (int64_t)(t + tstep) * H + c));
+      for (int i = 0; i < CPL; ++i) {
+        cp_async_16(dst + i * 512, reinterpret_cast<const uint4*>(xin + (int64_t)t * H) + lane + 32 * i, true);
+        cp_async_16(dst + H * 2 + i * 512, reinterpret_cast<const uint4*>(dyin + (int64_t)t * H) + lane + 32 * i, true);
       }
+    }
+    cp_async_commit();   // committed even when empty: the group count per iteration stays uniform
+  };
+#pragma unroll
+  for (int s = 0; s < kLnStages - 1; ++s) issue(t0 + s * tstep, s);
+  float nmu = 0.f, nrs = 0.f;
+  if (t0 < T) {
+    nmu = mean[t0];
+    nrs = rstd[t0];
+  }
+  int stage = 0;
+  for (int t = t0; t < T; t += tstep) {
+    cp_async_wait<kLnStages - 2>();   // this token's copies (the oldest group) have landed
+    const uint8_t* src = ln_smem + warp * (kLnStages * kLnStageBytes) + stage * kLnStageBytes + lane * 16;
+    uint4 xr[CPL], dr[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      xr[i] = *reinterpret_cast<const uint4*>(src + i * 512);
+      dr[i] = *reinterpret_cast<const uint4*>(src + H * 2 + i * 512);
+    }
+    // refill the stage consumed in the previous iteration with the token kLnStages - 1 steps ahead
+    issue(t + (kLnStages - 1) * tstep, stage == 0 ? kLnStages - 1 : stage - 1);
+    const float mu = nmu, rs = nrs;
+    if (t + tstep < T) {
       nmu = mean[t + tstep];
       nrs = rstd[t + tstep];
     }
-    ln_bwd_row(xhat, dy, rs, gamma, lane, dgam, dbet);
+    float xhat[CPL][8], dy[CPL][8];
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int c = 4 * (lane + 32 * i);
-      *reinterpret_cast<uint2*>(dx + (int64_t)t * H + c) = f4_to_bf16x4(dy[i]);
-      float4 m = dy[i];
+    for (int i = 0; i < CPL; ++i) {
+      unpack8(xr[i], xhat[i]);
+      unpack8(dr[i], dy[i]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        xhat[i][k] = (xhat[i][k] - mu) * rs;
+        dgam[i][k] = fmaf(dy[i][k], xhat[i][k], dgam[i][k]);
+        dbet[i][k] += dy[i][k];
+        dy[i][k] *= gam[i][k];
+        s1 += dy[i][k];
+        s2 = fmaf(dy[i][k], xhat[i][k], s2);
+      }
+    }
+    const float c1 = warp_sum(s1) * (1.0f / H), c2 = warp_sum(s2) * (1.0f / H);
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const int c = 8 * (lane + 32 * i);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dy[i][k] = rs * (dy[i][k] - c1 - xhat[i][k] * c2);
+      *(reinterpret_cast<uint4*>(dx + (int64_t)t * H) + lane + 32 * i) = pack8(dy[i]);
       if (dxm != nullptr) {
         const uint32_t base = (uint32_t)t * H + c;
-        bool k0_, k1_, k2_, k3_;
-        dropout_keep4(seed, base, thr, k0_, k1_, k2_, k3_);
-        m.x = k0_ ? m.x * scale : 0.f;
-        m.y = k1_ ? m.y * scale : 0.f;
-        m.z = k2_ ? m.z * scale : 0.f;
-        m.w = k3_ ? m.w * scale : 0.f;
-        *reinterpret_cast<uint2*>(dxm + (int64_t)t * H + c) = f4_to_bf16x4(m);
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+          bool k0, k1, k2, k3;
+          dropout_keep4(seed, base + 4 * hq, thr, k0, k1, k2, k3);
+          dy[i][4 * hq + 0] = k0 ? dy[i][4 * hq + 0] * scale : 0.f;
+          dy[i][4 * hq + 1] = k1 ? dy[i][4 * hq + 1] * scale : 0.f;
+          dy[i][4 * hq + 2] = k2 ? dy[i][4 * hq + 2] * scale : 0.f;
+          dy[i][4 * hq + 3] = k3 ? dy[i][4 * hq + 3] * scale : 0.f;
+        }
+        *(reinterpret_cast<uint4*>(dxm + (int64_t)t * H) + lane + 32 * i) = pack8(dy[i]);
       }
-      f4_acc(dbia[i], m);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dbia[i][k] += dy[i][k];
     }
+    stage = stage == kLnStages - 1 ? 0 : stage + 1;
   }
-  block_reduce_cols_atomic(dgam, dgamma, sh);
-  block_reduce_cols_atomic(dbet, dbeta, sh);
-  if (dbias != nullptr) block_reduce_cols_atomic(dbia, dbias, sh);
+  cp_async_wait<0>();
+  float* sh = reinterpret_cast<float*>(ln_smem);
+  block_reduce_cols8_atomic(dgam, dgamma, sh);
+  block_reduce_cols8_atomic(dbet, dbeta, sh);
+  if (dbias != nullptr) block_reduce_cols8_atomic(dbia, dbias, sh);
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -472,8 +595,20 @@ extern "C" int nbest_ln_fwd(nbest_ctx* ctx, const void* x_bf16, const float* gam
   NBEST_CHECK_ARG(ctx, hidden == H, "hidden must be 768");
   NBEST_CHECK_ARG(ctx, x_bf16 && gamma && beta && y_bf16, "null pointer");
   if (T <= 0) return NBEST_OK;
-  ln_fwd_kernel<<<(T + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x_bf16), gamma, beta, eps, T, reinterpret_cast<__nv_bfloat16*>(y_bf16), mean, rstd);
+  static int rows = 0;
+  if (rows == 0) {
+    const char* e = getenv("NBEST_LN_FWD_ROWS");
+    rows = e ? atoi(e) : 2;
+    if (rows != 1 && rows != 2 && rows != 4) rows = 2;
+  }
+  const int rows_per_block = kWarpsPerBlock * rows;
+  const int blocks = (T + rows_per_block - 1) / rows_per_block;
+  auto* xi = reinterpret_cast<const __nv_bfloat16*>(x_bf16);
+  auto* yo = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (rows == 1) ln_fwd_kernel<1><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, yo, mean, rstd);
+  else if (rows == 2) ln_fwd_kernel<2><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, yo, mean, rstd);
+  else ln_fwd_kernel<4><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, yo, mean, rstd);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
@@ -489,7 +624,12 @@ extern "C" int nbest_ln_bwd(nbest_ctx* ctx, const void* dy_bf16, const void* x_b
   if (T <= 0) return NBEST_OK;
   int blocks = (T + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (blocks > ctx->num_sms) blocks = ctx->num_sms;   // one block per SM (register-bound); fewer blocks = fewer column atomics
-  ln_bwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  static bool attr = false;
+  if (!attr) {
+    NBEST_CHECK_CUDA(ctx, cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnBwdSmem));
+    attr = true;
+  }
+  ln_bwd_kernel<<<blocks, kWarpsPerBlock * 32, kLnBwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16), mean, rstd, gamma, T,
       reinterpret_cast<__nv_bfloat16*>(dx_bf16), p_drop > 0.f ? reinterpret_cast<__nv_bfloat16*>(dx_masked_bf16) : nullptr,
       drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed, dgamma, dbeta, dbias);

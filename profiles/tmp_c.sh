@@ -1,1 +1,1 @@
-timeout -s KILL 600 python -m pytest tests -q -m gpu -x 2>&1 | tail -8
+for r in 1 2 4; do echo "rows=$r"; NBEST_LN_FWD_ROWS=$r timeout -s KILL 120 python profiles/ln_micro.py | grep -E "ln_fwd|copy"; done
