@@ -194,6 +194,18 @@ int nbest_stc_head_bwd(nbest_ctx* ctx, const float* dlogits, const float* cls, c
 int nbest_cls_scatter(nbest_ctx* ctx, const float* dcls, const int32_t* cu_seqlens, int B, int T, int hidden,
                       void* dx_bf16, void* stream);
 
+/* ---- K10b: epoch metrics on the device ------------------------------------------------------------------------
+ * Replaces the per-sample host loop of train_epoch / eval_epoch (n_best_asr_bert.py:283-288, 335-350) that calls
+ * pred_one_sample (:198-215), filter_informative (:218-229), update_f1 (utils/fscore.py:2-11) and compares label sets.
+ * decode [B,n_bottom] uint8 is the head kernel's prediction bitmap, labels [B,n_bottom] fp32 the gold multi-hot of
+ * collate_fn (utils/dataset/tod_asr_util.py:118-126; labels missing from label2idx sit in the <unk> column 1 and so
+ * count as false negatives, as their strings do in the reference). col_mask [n_bottom] uint8 (nullable) keeps the
+ * "informative" columns of the ontology filter (applied to predictions and gold alike, :338-340).
+ * counters[4] (int64, accumulated, never reset here) += {TP, FP, FN, utterances whose label sets match exactly};
+ * counters[4] is only read by the host once per epoch. */
+int nbest_stc_metrics(nbest_ctx* ctx, const uint8_t* decode, const float* labels, const uint8_t* col_mask, int B,
+                      int n_bottom, long long* counters, void* stream);
+
 /* ---- K11: fused multi-tensor BertAdam ---------------------------------------------------------------------- */
 /* BertAdam.step (models/optimization.py:237-302) with WarmupLinearSchedule (:162-171) and per-tensor
  * clip_grad_norm_ (:270-271) over one flat fp32 parameter buffer. seg[] (device) describes the tensors. */

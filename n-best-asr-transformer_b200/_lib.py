@@ -56,6 +56,7 @@ _SIGNATURES = {
     "nbest_stc_head_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(Hierarchy), _f32, _u32, _vp, _vp,
                                      _vp, C.c_int, _vp]),
     "nbest_cls_scatter": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "nbest_stc_metrics": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "nbest_bertadam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _f64, _f32, _f32,
                                       _f32, _f32, _vp]),
 }

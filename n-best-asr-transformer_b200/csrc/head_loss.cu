@@ -296,28 +296,45 @@ stc_scores_bwd_kernel(const float* __restrict__ top_scores, const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ head backward
-// dW[c,:] += sum_b dl[b,c] * drop_g(c)(f[b,:]),  dbias[c] += sum_b dl[b,c]       (one block per column)
-__global__ void __launch_bounds__(256)
+// dW[c,:] += sum_b dl[b,c] * drop_g(c)(f[b,:]),  dbias[c] += sum_b dl[b,c]
+// grid (column, batch split): 192 threads own four consecutive features each (one dropout quad per utterance), the
+// batch is cut into kWgradSplits slices that meet in fp32 red.add on the flat gradient (one column x 256 utterances in
+// a single block was a 100 us serial chain of dependent loads).
+constexpr int kWgradSplits = 8;
+__global__ void __launch_bounds__(192)
 stc_head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ cls, int B, Hier h, uint32_t thr,
                       float rscale, uint32_t seed, float* __restrict__ dW, float* __restrict__ dbias) {
   const int c = blockIdx.x;
   const int g = h.col_group[c];
-  float acc[3] = {0.f, 0.f, 0.f};
+  const int per = (B + kWgradSplits - 1) / kWgradSplits;
+  const int b0 = blockIdx.y * per, b1 = min(B, b0 + per);
+  const int d = 4 * threadIdx.x;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float sb = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float dl = dlogits[(int64_t)b * h.n_cols + c];
+#pragma unroll 4
+  for (int b = b0; b < b1; ++b) {
+    const float dl = __ldg(dlogits + (int64_t)b * h.n_cols + c);
+    float4 fv = __ldg(reinterpret_cast<const float4*>(cls + (int64_t)b * H + d));
     sb += dl;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int d = threadIdx.x + 256 * i;
-      float fv = cls[(int64_t)b * H + d];
-      if (thr) fv = dropout_keep(seed, ((uint32_t)g * (uint32_t)B + (uint32_t)b) * H + d, thr) ? fv * rscale : 0.f;
-      acc[i] += dl * fv;
+    if (thr) {
+      bool k0, k1, k2, k3;
+      dropout_keep4(seed, ((uint32_t)g * (uint32_t)B + (uint32_t)b) * H + d, thr, k0, k1, k2, k3);
+      fv.x = k0 ? fv.x * rscale : 0.f;
+      fv.y = k1 ? fv.y * rscale : 0.f;
+      fv.z = k2 ? fv.z * rscale : 0.f;
+      fv.w = k3 ? fv.w * rscale : 0.f;
     }
+    acc.x = fmaf(dl, fv.x, acc.x);
+    acc.y = fmaf(dl, fv.y, acc.y);
+    acc.z = fmaf(dl, fv.z, acc.z);
+    acc.w = fmaf(dl, fv.w, acc.w);
   }
-#pragma unroll
-  for (int i = 0; i < 3; ++i) dW[(int64_t)c * H + threadIdx.x + 256 * i] += acc[i];
-  if (threadIdx.x == 0) dbias[c] += sb;
+  if (b1 > b0) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dW + (int64_t)c * H + d), "f"(acc.x), "f"(acc.y), "f"(acc.z),
+                 "f"(acc.w)
+                 : "memory");
+    if (threadIdx.x == 0) atomicAdd(dbias + c, sb);
+  }
 }
 
 // dcls[b,:] (=|+=) sum_c dl[b,c] * W[c,:] * mask_g(c)[b,:]                          (one block per batch row)
@@ -352,6 +369,41 @@ __global__ void cls_scatter_kernel(const float* __restrict__ dcls, const int32_t
   const int b = blockIdx.x;
   __nv_bfloat16* row = dx + (int64_t)cu[b] * H;
   for (int d = threadIdx.x; d < H; d += blockDim.x) row[d] = __float2bfloat16_rn(dcls[(int64_t)b * H + d]);
+}
+
+// One warp per utterance: TP / FP / FN over the (optionally ontology-filtered) label columns and the exact-match flag.
+__global__ void __launch_bounds__(256)
+stc_metrics_kernel(const uint8_t* __restrict__ decode, const float* __restrict__ labels, const uint8_t* __restrict__ col_mask,
+                   int B, int nb, unsigned long long* __restrict__ counters) {
+  __shared__ unsigned int part[4];
+  if (threadIdx.x < 4) part[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b < B) {
+    unsigned int tp = 0, fp = 0, fn = 0;
+    for (int c = lane; c < nb; c += 32) {
+      if (col_mask != nullptr && col_mask[c] == 0) continue;
+      const bool p = decode[(int64_t)b * nb + c] != 0, g = labels[(int64_t)b * nb + c] > 0.5f;
+      tp += (p && g) ? 1u : 0u;
+      fp += (p && !g) ? 1u : 0u;
+      fn += (!p && g) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tp += __shfl_xor_sync(0xffffffffu, tp, o);
+      fp += __shfl_xor_sync(0xffffffffu, fp, o);
+      fn += __shfl_xor_sync(0xffffffffu, fn, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&part[0], tp);
+      atomicAdd(&part[1], fp);
+      atomicAdd(&part[2], fn);
+      atomicAdd(&part[3], (fp == 0 && fn == 0) ? 1u : 0u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 && part[threadIdx.x]) atomicAdd(&counters[threadIdx.x], (unsigned long long)part[threadIdx.x]);
 }
 
 inline uint32_t drop_threshold(float p) {
@@ -448,9 +500,21 @@ extern "C" int nbest_stc_head_bwd(nbest_ctx* ctx, const float* dlogits, const fl
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const uint32_t thr = drop_threshold(p_drop);
   const float rscale = 1.0f / (1.0f - p_drop);
-  stc_head_wgrad_kernel<<<h.n_cols, 256, 0, s>>>(dlogits, cls, B, h, thr, rscale, seed, dW, dbias);
+  stc_head_wgrad_kernel<<<dim3(h.n_cols, kWgradSplits), 192, 0, s>>>(dlogits, cls, B, h, thr, rscale, seed, dW, dbias);
   NBEST_CHECK_LAUNCH(ctx);
   stc_head_dgrad_kernel<<<B, 256, 0, s>>>(dlogits, W, B, h, thr, rscale, seed, dcls, accumulate_dcls);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
+extern "C" int nbest_stc_metrics(nbest_ctx* ctx, const uint8_t* decode, const float* labels, const uint8_t* col_mask, int B,
+                                 int n_bottom, long long* counters, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, decode && labels && counters, "null pointer");
+  NBEST_CHECK_ARG(ctx, B >= 0 && n_bottom > 0, "bad shape");
+  if (B == 0) return NBEST_OK;
+  stc_metrics_kernel<<<(B + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      decode, labels, col_mask, B, n_bottom, reinterpret_cast<unsigned long long*>(counters));
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }

@@ -1,0 +1,204 @@
+"""Pre-tokenised on-disk n-best data + pinned-memory prefetch.
+
+The reference re-tokenises every utterance word by word on the host in every epoch (utils/bert_xlnet_inputs.py:46-53,
+called twice per step from n_best_asr_bert.py:249-250) from the text-line files read by `read_wcn_data`
+(utils/dataset/tod_asr_util.py:43-71; line format `asr \\t<=>\\t transcript \\t<=>\\t l1;l2`). At > 20 k utterances/s per
+GPU that string work is the bottleneck, so it is done ONCE:
+
+  pretokenize(...)        runs the drop-in `prepare_inputs_for_roberta` over the file in chunks and stores the un-padded
+                          wordpiece ids of both streams, the segment boundary and the label indices as flat .npy arrays
+                          (CSR offsets) in a directory; ids are exactly what the reference would feed the encoder.
+  PretokenizedDataset     memory-maps that directory and assembles right-padded [B,S] int64 batches (the layout
+                          `model.forward` / `trainer.step` take) + the multi-hot labels with numpy slicing only.
+  Prefetcher              a background thread fills pinned host batches `depth` steps ahead and a side CUDA stream
+                          copies them to the device; the consumer's stream waits on the copy event, never on the host.
+"""
+import json
+import os
+import queue
+import threading
+
+import numpy as np
+import torch
+
+from .epoch import UNK_LABEL_IDX
+
+_ARRAYS = ("asr_ids", "asr_off", "asr_seg", "trans_ids", "trans_off", "trans_seg", "label_idx", "label_off")
+
+
+def read_wcn_lines(path):
+    """`read_wcn_data` without the pandas stratified sampler (utils/dataset/tod_asr_util.py:43-63)."""
+    asr, trans, labels = [], [], []
+    with open(path, "r") as f:
+        for line in f:
+            a, t, l = line.strip("\n\r").split("\t<=>\t")
+            asr.append(a.strip().split(" "))
+            trans.append(t.strip().split(" "))
+            labels.append([] if len(l) == 0 else l.strip().split(";"))
+    return asr, trans, labels
+
+
+def pretokenize(asr_seqs, trans_seqs, label_lists, tokenizer, opt, label2idx, out_dir, chunk=512):
+    """Tokenise once with the drop-in `prepare_inputs_for_roberta` and write the flat arrays. Returns out_dir."""
+    from .inputs import prepare_inputs_for_roberta
+    os.makedirs(out_dir, exist_ok=True)
+    flat = {k: [] for k in ("asr_ids", "asr_seg", "trans_ids", "trans_seg", "label_idx")}
+    lens = {k: [] for k in ("asr", "trans", "label")}
+    has_seg = True
+    for s in range(0, len(asr_seqs), chunk):
+        for name, seqs in (("asr", asr_seqs[s:s + chunk]), ("trans", trans_seqs[s:s + chunk])):
+            ids, seg, ln = prepare_inputs_for_roberta(list(seqs), tokenizer, opt, "cpu", pinned=False)
+            ids = ids.numpy()
+            has_seg = has_seg and seg is not None
+            for i, n in enumerate(ln):
+                flat[name + "_ids"].append(ids[i, :n].astype(np.int32))
+                # segment ids are 0 ... 0 1 ... 1 (bert_xlnet_inputs.py:75-85): the position of the first 1 is enough
+                flat[name + "_seg"].append(int(np.argmax(seg[i, :n].numpy() > 0)) if seg is not None and bool((seg[i, :n] > 0).any()) else n)
+                lens[name].append(n)
+        for labels in label_lists[s:s + chunk]:
+            idx = [label2idx.get(l, UNK_LABEL_IDX) for l in labels]
+            flat["label_idx"].append(np.asarray(idx, dtype=np.int32))
+            lens["label"].append(len(idx))
+    cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.int32)
+    off = lambda ls: np.concatenate([[0], np.cumsum(ls)]).astype(np.int64)
+    arrays = dict(asr_ids=cat(flat["asr_ids"]), asr_off=off(lens["asr"]), asr_seg=np.asarray(flat["asr_seg"], np.int32),
+                  trans_ids=cat(flat["trans_ids"]), trans_off=off(lens["trans"]), trans_seg=np.asarray(flat["trans_seg"], np.int32),
+                  label_idx=cat(flat["label_idx"]), label_off=off(lens["label"]))
+    for k, v in arrays.items():
+        np.save(os.path.join(out_dir, k + ".npy"), v)
+    meta = dict(format="nbest_b200.pretok.v1", n=len(asr_seqs), n_labels=len(label2idx), pad_token_id=int(tokenizer.pad_token_id),
+                has_segment_ids=bool(has_seg), pre_trained_model=getattr(opt, "pre_trained_model", None),
+                without_system_act=bool(getattr(opt, "without_system_act", False)),
+                tod_pre_trained_model=bool(getattr(opt, "tod_pre_trained_model", None)))
+    with open(os.path.join(out_dir, "meta.json"), "w") as f:
+        json.dump(meta, f)
+    return out_dir
+
+
+class PretokenizedDataset:
+    def __init__(self, path, mmap=True):
+        self.meta = json.load(open(os.path.join(path, "meta.json")))
+        if self.meta.get("format") != "nbest_b200.pretok.v1":
+            raise ValueError("%s is not a pre-tokenised n-best directory" % path)
+        for k in _ARRAYS:
+            setattr(self, k, np.load(os.path.join(path, k + ".npy"), mmap_mode="r" if mmap else None))
+        self.n = int(self.meta["n"])
+        self.n_labels = int(self.meta["n_labels"])
+        self.pad = int(self.meta["pad_token_id"])
+        self.has_seg = bool(self.meta["has_segment_ids"])
+
+    def __len__(self):
+        return self.n
+
+    def _stream(self, ids, off, seg_start, idx, pinned):
+        lens = (off[idx + 1] - off[idx]).astype(np.int64)
+        S = int(lens.max())
+        out = torch.full((len(idx), S), self.pad, dtype=torch.int64)
+        seg = torch.zeros((len(idx), S), dtype=torch.int64) if self.has_seg else None
+        o, sg = out.numpy(), (seg.numpy() if seg is not None else None)
+        for r, (i, n) in enumerate(zip(idx, lens)):
+            o[r, :n] = ids[off[i]:off[i] + n]
+            if sg is not None:
+                sg[r, seg_start[i]:n] = 1
+        if pinned:
+            out = out.pin_memory()
+            seg = seg.pin_memory() if seg is not None else None
+        return out, seg, [int(x) for x in lens]
+
+    def batch(self, indices, pinned=True):
+        """dict(ids, seg, lens, trans_ids, trans_seg, trans_lens, labels): host tensors in the reference's padded layout
+        (utils/bert_xlnet_inputs.py:91-102) — bit-identical to tokenising these utterances again."""
+        idx = np.asarray(indices, dtype=np.int64)
+        ids, seg, lens = self._stream(self.asr_ids, self.asr_off, self.asr_seg, idx, pinned)
+        tids, tseg, tlens = self._stream(self.trans_ids, self.trans_off, self.trans_seg, idx, pinned)
+        labels = torch.zeros((len(idx), self.n_labels), dtype=torch.float32)
+        ln = labels.numpy()
+        for r, i in enumerate(idx):
+            ln[r, self.label_idx[self.label_off[i]:self.label_off[i + 1]]] = 1.0
+        if pinned:
+            labels = labels.pin_memory()
+        return dict(ids=ids, seg=seg, lens=lens, trans_ids=tids, trans_seg=tseg, trans_lens=tlens, labels=labels, index=idx)
+
+
+def epoch_order(n, batch_size, shuffle, seed, epoch, rank=0, world=1, drop_last=False):
+    """Batches of sample indices for one epoch; with world > 1 every rank takes a disjoint, equally sized slice of each
+    global batch (the data-parallel split of SURVEY §8(e))."""
+    order = np.arange(n)
+    if shuffle:
+        order = np.random.default_rng(seed + 1000003 * epoch).permutation(n)
+    gb = batch_size * world
+    out = []
+    for s in range(0, n, gb):
+        chunk = order[s:s + gb]
+        if len(chunk) < gb and (drop_last or world > 1):
+            if drop_last or len(chunk) < world:
+                break
+            chunk = chunk[:len(chunk) // world * world]
+        per = len(chunk) // world
+        out.append(chunk[rank * per:(rank + 1) * per])
+    return out
+
+
+class Prefetcher:
+    """Iterates device batches of a PretokenizedDataset: host assembly in a background thread (`depth` batches ahead, pinned
+    memory), H2D on a side stream. Yields dict(ids, seg, trans_ids, trans_seg, labels: device tensors; lens, trans_lens:
+    host lists; index). Usable as `for b in Prefetcher(...)`; one pass = one epoch."""
+
+    _KEYS = ("ids", "seg", "trans_ids", "trans_seg", "labels")
+
+    def __init__(self, dataset, batches, device, depth=3):
+        self.ds, self.batches, self.depth = dataset, list(batches), max(1, int(depth))
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+
+    def __len__(self):
+        return len(self.batches)
+
+    def _producer(self, q):
+        try:
+            for idx in self.batches:
+                q.put(self.ds.batch(idx, pinned=self.cuda))
+        except BaseException as e:          # surfaced in the consumer
+            q.put(e)
+        q.put(None)
+
+    def _to_device(self, host):
+        if not self.cuda:
+            return host, None
+        out = dict(host)
+        with torch.cuda.stream(self.stream):
+            for k in self._KEYS:
+                if host[k] is not None:
+                    out[k] = host[k].to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        out["_host"] = host                 # keeps the pinned source alive until the copy has been consumed
+        return out, ev
+
+    def __iter__(self):
+        q = queue.Queue(maxsize=self.depth)
+        th = threading.Thread(target=self._producer, args=(q,), daemon=True)
+        th.start()
+        pending = []
+        done = False
+        while True:
+            while not done and len(pending) < 2:
+                item = q.get()
+                if item is None:
+                    done = True
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                pending.append(self._to_device(item))
+            if not pending:
+                break
+            batch, ev = pending.pop(0)
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+                for k in self._KEYS:
+                    if batch[k] is not None:
+                        batch[k].record_stream(torch.cuda.current_stream(self.device))
+            batch.pop("_host", None)
+            yield batch
+        th.join()

@@ -330,6 +330,16 @@ def stc_head_bwd(dlogits, cls, W, hier, dW, dbias, dcls, accumulate_dcls=False, 
                                                 _stream()))
 
 
+def stc_metrics(decode, labels, counters, col_mask=None):
+    """counters[4] (int64, device) += TP, FP, FN, exact matches of this batch (see nbest_stc_metrics)."""
+    ctx = _ctx(decode)
+    assert decode.dtype == torch.uint8 and labels.dtype == torch.float32 and counters.dtype == torch.int64
+    assert decode.is_contiguous() and labels.is_contiguous() and decode.shape == labels.shape
+    with _Timed('stc_metrics', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_stc_metrics(ctx.handle, _p(decode), _p(labels), _p(col_mask), decode.shape[0],
+                                               decode.shape[1], _p(counters), _stream()))
+
+
 def cls_scatter(dcls, cu_seqlens, B, T, dx):
     ctx = _ctx(dcls)
     with _Timed('cls_scatter', 0.0, 0.0):

@@ -248,7 +248,72 @@ def packing_case(prepare_inputs_for_roberta, m):
     print("packing fixture: ids", out["ids_default"].shape, "lens", out["lens_default"][:8])
 
 
+def epoch_case(nb, m):
+    """A1 / A11 / A10 / A12 golden: on 48 real lines of the shipped `valid` file run the reference's own collate_fn
+    (utils/dataset/tod_asr_util.py:86-132), and on seeded random scores its pred_one_sample, filter_informative and
+    update_f1 / compute_f1 -> gold multi-hots, predicted label strings and the epoch counters our device metrics must hit."""
+    from utils.dataset.tod_asr_util import collate_fn
+    from utils.fscore import update_f1, compute_f1
+    lines = open(os.path.join(REF, "dstc2_data/processed_data/raw/valid")).read().strip("\n").split("\n")
+    pick = [i for i, l in enumerate(lines) if l.split("\t<=>\t")[2].strip()][:40] + \
+        [i for i, l in enumerate(lines) if any(x not in m["label2idx"] for x in l.split("\t<=>\t")[2].strip().split(";"))][:8]
+    batch = []
+    for i in pick:
+        a, t, l = lines[i].strip("\n\r").split("\t<=>\t")
+        batch.append((a.strip().split(" "), t.strip().split(" "), [] if len(l) == 0 else l.strip().split(";")))
+    labels, in_seqs, trans_seqs, label_lists = collate_fn(batch, m, 512, torch.device("cpu"))
+    hier = O.Hierarchy({int(k): [int(x) for x in v] for k, v in m["top2bottom_dict"].items()},
+                       [int(i) for i, l in m["idx2label"].items() if l.endswith("NONE")])
+    g = torch.Generator().manual_seed(77)
+    B = len(batch)
+    top = torch.rand(B, hier.n_top, generator=g) * 0.51          # ~2 % spurious act-slots above the 0.5 threshold
+    # make the gold act-slots likely to fire so that TP is well populated
+    b2t = m["bottom2top_mat"] if "bottom2top_mat" in m else None
+    bottoms, flat = {}, []
+    for k in sorted(hier.top2bottom):
+        ids = hier.top2bottom[k]
+        if len(ids) > 1:
+            bottoms["lin_%d" % k] = torch.softmax(3 * torch.randn(B, len(ids), generator=g), -1)
+            flat.append(bottoms["lin_%d" % k])
+    for i, ll in enumerate(label_lists):           # bias towards the gold labels (two thirds of them)
+        for l in ll:
+            if l in m["label2idx"] and (i + len(l)) % 3 != 0:
+                bi = m["label2idx"][l]
+                for k, ids in hier.top2bottom.items():
+                    if bi in ids:
+                        top[i, k] = 0.9
+                        if len(ids) > 1:
+                            bottoms["lin_%d" % k][i] = 0.01
+                            bottoms["lin_%d" % k][i, ids.index(bi)] = 0.9
+    opt = Namespace()
+    ontology = json.load(open(os.path.join(REF, "dstc2_data/processed_data/ontology_dstc2.json"))) \
+        if os.path.exists(os.path.join(REF, "dstc2_data/processed_data/ontology_dstc2.json")) else \
+        dict(informable=dict(food=["a", "b"], area=["x", "y"], pricerange=["p", "q"], name=["n"]))
+    preds, preds_f, counts, counts_f = [], [], [0, 0, 0, 0], [0, 0, 0, 0]
+    for i, (ts, gold) in enumerate(zip(top.tolist(), label_lists)):
+        pc = nb.pred_one_sample(i, ts, bottoms, m, opt)
+        preds.append(pc)
+        counts[:3] = update_f1(pc, gold, *counts[:3])
+        counts[3] += int(set(pc) == set(gold))
+        pf, gf = nb.filter_informative(pc, ontology), nb.filter_informative(gold, ontology)
+        preds_f.append(pf)
+        counts_f[:3] = update_f1(pf, gf, *counts_f[:3])
+        counts_f[3] += int(set(pf) == set(gold if False else gf))
+    out = dict(labels=labels.numpy(), top=top.numpy(), bottom=torch.cat(flat, 1).numpy(),
+               counts=np.array(counts), counts_filtered=np.array(counts_f),
+               prf=np.array(compute_f1(*counts[:3])), prf_filtered=np.array(compute_f1(*counts_f[:3])),
+               meta=json.dumps(dict(label_lists=label_lists, preds=preds, preds_filtered=preds_f, ontology=ontology,
+                                    label2idx=m["label2idx"], raw_in=[" ".join(x) for x in in_seqs],
+                                    raw_trans=[" ".join(x) for x in trans_seqs])))
+    np.savez_compressed(os.path.join(GOLD, "epoch_valid48.npz"), **out)
+    print("epoch fixture: B", B, "counts", counts, "filtered", counts_f, "unk golds", int(labels[:, 1].sum()))
+
+
 def main():
+    if "--epoch-only" in sys.argv:
+        refmods = import_reference()
+        m = torch.load(os.path.join(REF, "dstc2_data/processed_data/raw/memory.pt"))
+        return epoch_case(refmods[0], m)
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -266,6 +331,7 @@ def main():
     case("xlmr_l2_small", O.EncoderConfig.xlmr_base(vocab_size=1200, layers=2, max_position=98), hier, refmods, B=4,
          max_len=30, seed=13, add_l2=True, keep_grads=keep[:4])
     packing_case(refmods[4], m)
+    epoch_case(refmods[0], m)
 
 
 if __name__ == "__main__":

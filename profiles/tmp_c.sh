@@ -1,1 +1,1 @@
-for r in 1 2 4; do echo "rows=$r"; NBEST_LN_FWD_ROWS=$r timeout -s KILL 120 python profiles/ln_micro.py | grep -E "ln_fwd|copy"; done
+timeout -s KILL 600 python -m pytest tests/test_epoch_gpu.py tests/test_kernels_gpu.py -q -m gpu -x 2>&1 | tail -25
