@@ -258,10 +258,15 @@ def main():
         raise SystemExit("non-finite loss in the benchmark step")
 
     # ---- per-kernel roofline leg: two instrumented steps (CUDA events around every launch of ours)
+    # (the per-bucket BertAdam normally runs on a side stream under the backward; the instrumented steps serialise it on
+    #  the main stream so that the CUDA events around each launch measure that launch)
+    overlap = trainer.overlap_optimizer
+    trainer.overlap_optimizer = False
     ops.profile_start()
     for i in range(2):
         step_dev(i)
     rec = ops.profile_stop()
+    trainer.overlap_optimizer = overlap
     agg = {}
     for name, t, fl, by, meta in rec:
         a = agg.setdefault(name, [0.0, 0.0, 0.0, 0])

@@ -70,6 +70,23 @@ def unbind_stream():
     _STREAM = None
 
 
+class on_stream:
+    """Context manager: launches made inside go to `stream` (a torch.cuda.Stream), whatever stream the step is bound to."""
+
+    def __init__(self, stream):
+        self.handle = C.c_void_p(stream.cuda_stream)
+
+    def __enter__(self):
+        global _STREAM
+        self.prev = _STREAM
+        _STREAM = self.handle
+
+    def __exit__(self, *exc):
+        global _STREAM
+        _STREAM = self.prev
+        return False
+
+
 def with_bound_stream(fn):
     """Decorator for the public entry points: bind the current stream once for all launches made inside."""
     import functools

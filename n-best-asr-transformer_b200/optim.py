@@ -178,6 +178,65 @@ class BertAdam(torch.optim.Optimizer):
         return {p: dict(step=s, next_m=self.flat.view(self.flat.m, i), next_v=self.flat.view(self.flat.v, i))
                 for p, s, i in zip(self._plist, self._steps, self._idx)}
 
+    # ------------------------------------------------------------------ bucketed step (overlapped with backward)
+    def set_buckets(self, segments):
+        """segments: (name, start, end) element ranges of the flat buffers, e.g. trainer.model_segments(). Afterwards
+        begin_bucketed_step() / step_bucket(name) / end_bucketed_step() update one bucket at a time — each as soon as its
+        gradients are final — instead of everything after the last gradient (same arithmetic as step(): clipping is per
+        tensor, models/optimization.py:270-271, so tensors can be stepped in any grouping)."""
+        self._bucket_segments = [(n, int(s), int(e)) for n, s, e in segments]
+        self._bucket_tables = None
+
+    def _active_list(self):
+        active = []
+        for p, i in zip(self._plist, self._idx):
+            a = p.grad is not None
+            if a and p.grad.data_ptr() != self.flat.grads.data_ptr() + 4 * self.flat.offsets[i]:
+                self.flat.view(self.flat.grads, i).copy_(p.grad)
+                p.grad = self.flat.view(self.flat.grads, i)
+            active.append(a)
+        return active
+
+    @torch.no_grad()
+    def begin_bucketed_step(self):
+        groups = self._hyper()
+        active = self._active_list()
+        sig = (tuple(active), tuple((g["lr"], g["weight_decay"]) for g in groups))
+        if getattr(self, "_bucket_tables", None) is None or sig != getattr(self, "_bucket_sig", None):
+            self._bucket_tables = {}
+            for name, s, e in self._bucket_segments:
+                spec = []
+                for p, g, i, a in zip(self._plist, groups, self._idx, active):
+                    off = self.flat.offsets[i]
+                    spec.append(dict(offset=off, numel=p.numel(), lr=g["lr"], weight_decay=g["weight_decay"],
+                                     active=a and s <= off < e))
+                if any(x["active"] for x in spec):
+                    self._bucket_tables[name] = build_adam_tables(spec, self._plist[0].device)
+            self._bucket_sig = sig
+        self.flat.ensure_moments()
+        steps = {s for a, s in zip(active, self._steps) if a}
+        if len(steps) > 1:
+            raise RuntimeError("BertAdam: parameters became active at different steps; per-tensor step counts diverged")
+        g0 = groups[0]
+        self._bucket_sched = schedule_multiplier(steps.pop(), g0["t_total"], g0["warmup"], g0["schedule"]) if steps else 0.0
+        self._bucket_active = active
+
+    @torch.no_grad()
+    def step_bucket(self, name):
+        """Update the tensors of one bucket on the stream the caller has bound (ops.on_stream)."""
+        t = self._bucket_tables.get(name)
+        if t is None:
+            return
+        g0 = self.param_groups[0]
+        ops.bertadam_step(self.flat.params, self.flat.grads, self.flat.m, self.flat.v, self.flat.bf16, t["tensors"],
+                          t["n_tensors"], t["chunks"], t["n_chunks"], t["norms"], self._bucket_sched, g0["b1"], g0["b2"],
+                          g0["e"], g0["max_grad_norm"])
+
+    def end_bucketed_step(self):
+        for k, a in enumerate(self._bucket_active):
+            if a:
+                self._steps[k] += 1
+
     @torch.no_grad()
     @ops.with_bound_stream
     def step(self, closure=None):

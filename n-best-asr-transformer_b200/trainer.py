@@ -115,26 +115,59 @@ class DataParallelTrainer:
     `losses` holds this rank's local terms (sum-reduced over its own utterances); `global_losses()` all-reduces them
     for logging (once per logging interval, not per step)."""
 
-    def __init__(self, model, optimizer, add_l2_loss=False, group=None):
+    def __init__(self, model, optimizer, add_l2_loss=False, group=None, overlap_optimizer=None):
         self.model, self.optimizer, self.add_l2_loss = model, optimizer, add_l2_loss
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.comm_stream = torch.cuda.Stream(device=model.device) if self.world > 1 else None
-        self.bucketer = GradBucketer(model.flat.grads, model_segments(model), group, self.comm_stream)
+        segments = model_segments(model)
+        self.bucketer = GradBucketer(model.flat.grads, segments, group, self.comm_stream)
         self.group = group
+        # BertAdam per bucket on a side stream, each bucket as soon as its (all-reduced) gradients are final: the HBM-bound
+        # update of layer l then runs under the tensor-bound backward GEMMs of the layers below it instead of after them
+        # (single GPU: measured neutral — the update competes with the wgrad GEMMs for HBM — so it is on by default only
+        #  for data-parallel runs, where it also takes the update off the tail behind the last all-reduce)
+        if overlap_optimizer is None:
+            env = os.environ.get("NBEST_OVERLAP_ADAM")
+            overlap_optimizer = (self.world > 1) if env is None else env != "0"
+        self.overlap_optimizer = bool(overlap_optimizer) and hasattr(optimizer, "set_buckets") and \
+            getattr(optimizer, "flat", None) is model.flat
+        self._bucket_names = {n for n, _, _ in segments}
+        if self.overlap_optimizer:
+            optimizer.set_buckets(segments)
+            self.opt_stream = torch.cuda.Stream(device=model.device)
+
+    def _grad_ready(self, name):
+        self.bucketer.reduce(name)                       # DP: all-reduce on the comm stream after what is enqueued so far
+        if not self.overlap_optimizer or name not in self._bucket_names:
+            return
+        ev = torch.cuda.Event()
+        ev.record(self.comm_stream if self.world > 1 else torch.cuda.current_stream())
+        self.opt_stream.wait_event(ev)
+        with ops.on_stream(self.opt_stream):
+            self.optimizer.step_bucket(name)
 
     @ops.with_bound_stream
     def step(self, ids, labels, trans_ids=None, seg=None, trans_seg=None, lens=None, trans_lens=None):
         m = self.model
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())     # zeroed grads / previous step are visible
-        m._grad_ready_hook = self.bucketer.reduce if self.world > 1 else None
+        if self.overlap_optimizer:
+            self.opt_stream.wait_stream(torch.cuda.current_stream())      # the previous step's zero_grad is visible
+            self.optimizer.begin_bucketed_step()
+            m._grad_ready_hook = self._grad_ready
+        else:
+            m._grad_ready_hook = self.bucketer.reduce if self.world > 1 else None
         try:
             losses, head = m.forward_loss_backward(ids, labels, trans_ids, seg, trans_seg, add_l2_loss=self.add_l2_loss,
                                                    mse_scale=1.0 / self.world, input_lens=lens, trans_input_lens=trans_lens)
         finally:
             m._grad_ready_hook = None
         self.bucketer.wait()
-        self.optimizer.step()
+        if self.overlap_optimizer:
+            torch.cuda.current_stream().wait_stream(self.opt_stream)
+            self.optimizer.end_bucketed_step()
+        else:
+            self.optimizer.step()
         self.optimizer.zero_grad()
         self.last_head = head
         return losses

@@ -1,1 +1,1 @@
-timeout -s KILL 600 python -m pytest tests/test_epoch_gpu.py tests/test_kernels_gpu.py -q -m gpu -x 2>&1 | tail -25
+timeout -s KILL 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
