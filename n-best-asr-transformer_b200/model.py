@@ -434,6 +434,10 @@ class TOD_ASR_Transformer_STC(nn.Module):
             dm = dprem if p_h > 0 else dpre
             ops.gemm(dm, w["h_wo"], b_mn_major=True, epilogue=ops.EPI_NONE, out=dctx)
             ops.gemm(dm, R(L.ctx), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_wo"])
+            # a window of short, non-persistent kernels (attention backward): the data-parallel trainer starts the pending
+            # gradient all-reduces here, so that they run next to kernels that shrink gracefully instead of next to the
+            # persistent GEMMs, whose CTA pairs would have to wait for the SMs the collective occupies
+            self._notify("slot")
             if compact:
                 ops.attn_cls_bwd(L.qkv, cu, kv, B_act, max_len, s.heads, T, L.ctx, dctx, L.lse, pk.B, dqkv, p_a, self._seed(l, 1))
                 # the residual branch reaches the layer input only at the CLS rows

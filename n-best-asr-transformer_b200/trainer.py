@@ -119,9 +119,16 @@ class DataParallelTrainer:
         self.model, self.optimizer, self.add_l2_loss = model, optimizer, add_l2_loss
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.comm_stream = torch.cuda.Stream(device=model.device) if self.world > 1 else None
-        segments = model_segments(model)
+        # Collective placement: a bucket whose gradients are final is not reduced at once but at the next "slot" the
+        # backward announces (just before an attention-backward window). NCCL's CTAs then share the GPU with many small
+        # CTAs; launched next to a persistent tcgen05 GEMM they would hold SMs that the GEMM's statically scheduled CTA
+        # pairs wait for (measured: dgrad GEMMs 22 % slower under overlap). One layer per bucket (28 MB) fits a window.
+        env_slots = os.environ.get("NBEST_COMM_SLOTS")
+        self.comm_slots = self.world > 1 and (env_slots is None or env_slots != "0")
+        segments = model_segments(model, 1 if (self.comm_slots and "NBEST_BUCKET_LAYERS" not in os.environ) else None)
         self.bucketer = GradBucketer(model.flat.grads, segments, group, self.comm_stream)
         self.group = group
+        self._pending = []
         # BertAdam per bucket on a side stream, each bucket as soon as its (all-reduced) gradients are final: the HBM-bound
         # update of layer l then runs under the tensor-bound backward GEMMs of the layers below it instead of after them
         # (single GPU: measured neutral — the update competes with the wgrad GEMMs for HBM — so it is on by default only
@@ -137,6 +144,20 @@ class DataParallelTrainer:
             self.opt_stream = torch.cuda.Stream(device=model.device)
 
     def _grad_ready(self, name):
+        if self.comm_slots:
+            if name == "slot" or name == "emb":
+                if name == "emb":
+                    self._pending.append(name)
+                pending, self._pending = self._pending, []
+                for n in pending:
+                    self._launch_bucket(n)
+            elif name in self._bucket_names:
+                self._pending.append(name)
+            return
+        if name != "slot":
+            self._launch_bucket(name)
+
+    def _launch_bucket(self, name):
         self.bucketer.reduce(name)                       # DP: all-reduce on the comm stream after what is enqueued so far
         if not self.overlap_optimizer or name not in self._bucket_names:
             return
@@ -156,12 +177,16 @@ class DataParallelTrainer:
             self.optimizer.begin_bucketed_step()
             m._grad_ready_hook = self._grad_ready
         else:
-            m._grad_ready_hook = self.bucketer.reduce if self.world > 1 else None
+            m._grad_ready_hook = self._grad_ready if self.world > 1 else None
+        self._pending = []
         try:
             losses, head = m.forward_loss_backward(ids, labels, trans_ids, seg, trans_seg, add_l2_loss=self.add_l2_loss,
                                                    mse_scale=1.0 / self.world, input_lens=lens, trans_input_lens=trans_lens)
         finally:
             m._grad_ready_hook = None
+        for n in self._pending:                          # (only if the backward never announced "emb")
+            self._launch_bucket(n)
+        self._pending = []
         self.bucketer.wait()
         if self.overlap_optimizer:
             torch.cuda.current_stream().wait_stream(self.opt_stream)
