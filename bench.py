@@ -162,6 +162,9 @@ def main():
     ap.add_argument("--l2", action="store_true", help="--add_l2_loss: transcript stream with gradients + MSE term")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropout", action="store_true")
+    ap.add_argument("--skip-transcript", action="store_true",
+                    help="do not run the transcript stream at all (without --add_l2_loss the reference computes it forward-only "
+                         "and never uses the result; default = run it, as the reference does)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -212,14 +215,21 @@ def main():
         stats.append((L.sum(), (L ** 2).sum(), Lt.sum(), (Lt ** 2).sum()))
     h2d_bytes = int(np.mean([sum(h[k].numel() * h[k].element_size() for k in keys) for h in host]))
 
+    skip_t = args.skip_transcript and not args.l2
+
     def step_dev(i):
         b = devb[i % NB]
+        if skip_t:
+            return trainer.step(b["ids"], b["labels"], None, b["seg"], None, b["lens"], None)
         return trainer.step(b["ids"], b["labels"], b["trans_ids"], b["seg"], b["trans_seg"], b["lens"], b["trans_lens"])
 
     def step_host(i):
         h = host[i % NB]
         d = {k: h[k].to(dev, non_blocking=True) for k in keys}
-        losses = trainer.step(d["ids"], d["labels"], d["trans_ids"], d["seg"], d["trans_seg"], h["lens"], h["trans_lens"])
+        if skip_t:
+            losses = trainer.step(d["ids"], d["labels"], None, d["seg"], None, h["lens"], None)
+        else:
+            losses = trainer.step(d["ids"], d["labels"], d["trans_ids"], d["seg"], d["trans_seg"], h["lens"], h["trans_lens"])
         return losses.cpu()                                         # D2H read of the step's loss terms (synchronises)
 
     def barrier():
@@ -300,7 +310,8 @@ def main():
                 args.batch, args.hyps, args.max_len, ", dense" if args.dense else "", ", add_l2_loss" if args.l2 else ""),
                 global_batch=world * args.batch, tokens_per_step_asr=float(T), tokens_per_step_transcript=float(Tt),
                 parallelism="dp%d" % world, dropout="off" if args.no_dropout else "0.1/0.1/0.3",
-                streams="asr fwd+bwd, transcript %s" % ("fwd+bwd" if args.l2 else "fwd only (as the reference)"),
+                streams="asr fwd+bwd, transcript %s" % ("fwd+bwd" if args.l2 else ("skipped (--skip-transcript)" if skip_t else
+                                                                                    "fwd only (as the reference)")),
                 l2_flush="per-step working set (activations + 438 MB fp32 weights + Adam state, > 4 GB) exceeds the 126 MB L2"),
             clocks=clocks,
             e2e=dict(value=utt / (ms_e2e / 1e3), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=16,
