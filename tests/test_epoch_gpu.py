@@ -178,3 +178,32 @@ def test_prefetcher_feeds_the_trainer_from_pretokenized_data(tmp_path):
         n += len(b["lens"])
     mean_loss, _, _ = metrics.result()
     assert n == 48 and np.isfinite(mean_loss) and metrics.counters[4].item() == 48
+
+
+def test_bucketed_adam_on_side_stream_equals_single_step_update():
+    """DataParallelTrainer(overlap_optimizer=True) steps BertAdam bucket by bucket on a side stream as soon as a bucket's
+    gradients are final (the data-parallel default); it must land on the same weights, moments and step counters as the
+    single optimizer.step() after the backward (clipping is per tensor, so the grouping cannot matter)."""
+    from nbest_b200 import epoch as E
+    from nbest_b200.trainer import DataParallelTrainer
+    res = []
+    for overlap in (False, True):
+        model, optim, opt, memory, meta, raw_in, raw_trans, *_ = _setup(layers=3)
+        tr = DataParallelTrainer(model, optim, overlap_optimizer=overlap)
+        assert tr.overlap_optimizer == overlap
+        model.train()
+        for labels, rin, rtr, ll in _batches(E, meta, raw_in, raw_trans, 16):
+            from nbest_b200.inputs import prepare_inputs_for_roberta as prep
+            ids, seg, lens = prep(rin, opt.tokenizer, opt, "cuda")
+            tids, tseg, tlens = prep(rtr, opt.tokenizer, opt, "cuda")
+            losses = tr.step(ids, labels.cuda(), tids, seg, tseg, lens, tlens)
+        # a step without the transcript stream (the reference never uses it when --add_l2_loss is off)
+        losses = tr.step(ids, labels.cuda(), None, seg, None, lens, None)
+        torch.cuda.synchronize()
+        assert torch.isfinite(losses).all()
+        res.append((model.flat.params.clone(), optim.flat.m.clone(), optim.flat.v.clone(), list(optim._steps), losses.clone()))
+    a, b = res
+    cos = lambda x, y: float((x.double() @ y.double()) / (x.double().norm() * y.double().norm()))
+    assert a[3] == b[3] and max(a[3]) == 4
+    assert cos(a[0], b[0]) > 1 - 1e-7 and cos(a[1], b[1]) > 0.999 and cos(a[2], b[2]) > 0.999
+    assert torch.allclose(a[4], b[4], rtol=2e-3)
