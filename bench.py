@@ -97,8 +97,10 @@ def run_reference_arm(args):
     v = n_utt / med
     line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=med * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="bert-base n-best STC train step, 5 hyps, max_len 128, both streams, dropout on",
-                            batch_per_step=n_utt, device="cpu"),
+                config=dict(workload="BERT-base-uncased n-best STC bf16 packed varlen, batch %d/GPU, %d hyps, max_len %d" % (
+                    args.batch, args.hyps, args.max_len), global_batch=args.batch, parallelism="cpu",
+                    sample="each timed step = a %d-utterance slice of that workload (same generator, both streams, dropout on, "
+                           "fp32, BertAdam) on the host cores" % n_utt, device="cpu"),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind="port",
                                   sample="%d-utterance batches of the same generator, %d timed steps" % (n_utt, args.steps)),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))

@@ -280,3 +280,39 @@ def test_cls_only_last_layer_equals_full_last_layer(l2):
         if "key.bias" in n:
             continue
         assert _cos(a[4][n], b[4][n]) > 0.9995, (n, _cos(a[4][n], b[4][n]))
+
+
+def test_full_size_batch_256_gradient_is_additive_over_a_data_parallel_split():
+    """BASELINE configs[1] size (BERT-base, B = 256, 5-best, max_len 128) through the CUDA path, checked by a
+    size-independent property instead of the (hours-long) CPU oracle: every class-loss term is SUM-reduced over the
+    batch (n_best_asr_bert.py:572-573), so loss terms and gradients of the full batch must equal the sum over a 2-way
+    data-parallel split — the identity the bucketed all-reduce relies on. Dropout off."""
+    from oracle import stc_oracle as O
+    from nbest_b200.synth import synth_batch
+    hier_o, hj = _hier()
+    cfg = O.EncoderConfig.bert_base()
+    params = O.init_params(cfg, hier_o, seed=5, style="hf")
+    batch = synth_batch(cfg.kind, cfg.vocab_size, hier_o, B=256, n_hyps=5, max_len=128, seed=999)
+    model = _build(cfg, hier_o, hj, params)
+    model.train()
+    keys = ("ids", "labels", "trans_ids", "seg", "trans_seg")
+
+    def run(sl):
+        model.zero_grad()
+        d = {k: batch[k][sl].cuda() for k in keys}
+        # trim the padding of the slice to its own maximum, as a rank of the data-parallel job would see it
+        S = int((d["ids"] > 0).sum(1).max())
+        St = int((d["trans_ids"] > 0).sum(1).max())
+        losses, ho = model.forward_loss_backward(d["ids"][:, :S].contiguous(), d["labels"], d["trans_ids"][:, :St].contiguous(),
+                                                 d["seg"][:, :S].contiguous(), d["trans_seg"][:, :St].contiguous(),
+                                                 add_l2_loss=False)
+        return losses.clone(), model.flat.grads.clone(), ho.top.clone()
+
+    l_full, g_full, top_full = run(slice(0, 256))
+    l_a, g_a, top_a = run(slice(0, 128))
+    l_b, g_b, top_b = run(slice(128, 256))
+    assert torch.isfinite(g_full).all() and float(l_full[1]) > 0
+    assert _rel(l_a + l_b, l_full) < 2e-3
+    assert _rel(torch.cat([top_a, top_b]), top_full) < 5e-3                  # per-utterance results do not depend on the batch
+    assert _cos(g_a + g_b, g_full) > 0.9999
+    assert abs(float((g_a + g_b).norm() / g_full.norm()) - 1.0) < 5e-3
