@@ -338,30 +338,49 @@ stc_head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict
 }
 
 // dcls[b,:] (=|+=) sum_c dl[b,c] * W[c,:] * mask_g(c)[b,:]                          (one block per batch row)
-__global__ void __launch_bounds__(256)
+// 192 threads own four consecutive features each. A column's dropout mask only depends on its GROUP (the 11 nn.Linear
+// calls of hierarchical_classifier.py:41,46 each drew one mask of the feature), so the <= 16 group masks are hashed once
+// per thread (one quad each) instead of once per column and feature (171 x 3 hashes before).
+__global__ void __launch_bounds__(192)
 stc_head_dgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ W, int B, Hier h, uint32_t thr,
                       float rscale, uint32_t seed, float* __restrict__ dcls, int accumulate) {
   __shared__ float dl[kMaxCols];
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < h.n_cols; c += blockDim.x) dl[c] = dlogits[(int64_t)b * h.n_cols + c];
-  __syncthreads();
-  float acc[3] = {0.f, 0.f, 0.f};
-  for (int c = 0; c < h.n_cols; ++c) {
-    const int g = h.col_group[c];
-    const float v = dl[c];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int d = threadIdx.x + 256 * i;
-      float w = __ldg(W + (int64_t)c * H + d);
-      if (thr) w = dropout_keep(seed, ((uint32_t)g * (uint32_t)B + (uint32_t)b) * H + d, thr) ? w * rscale : 0.f;
-      acc[i] += v * w;
+  const int d = 4 * threadIdx.x;
+  uint64_t keep_bits = ~0ull;          // bit 4 g + i: feature d + i survives group g's mask
+  if (thr) {
+    keep_bits = 0;
+    const int ng = h.n_groups + 1 < 16 ? h.n_groups + 1 : 16;   // host checks n_groups + 1 <= 16 (4 keep bits per group)
+    for (int g = 0; g < ng; ++g) {
+      bool k0, k1, k2, k3;
+      dropout_keep4(seed, ((uint32_t)g * (uint32_t)B + (uint32_t)b) * H + d, thr, k0, k1, k2, k3);
+      keep_bits |= (uint64_t)((k0 ? 1u : 0u) | (k1 ? 2u : 0u) | (k2 ? 4u : 0u) | (k3 ? 8u : 0u)) << (4 * g);
     }
   }
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    float* o = dcls + (int64_t)b * H + threadIdx.x + 256 * i;
-    *o = accumulate ? *o + acc[i] : acc[i];
+  __syncthreads();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int c = 0; c < h.n_cols; ++c) {
+    const uint32_t m = (uint32_t)(keep_bits >> (4 * h.col_group[c])) & 15u;
+    const float v = dl[c];
+    const float4 w = __ldg(reinterpret_cast<const float4*>(W + (int64_t)c * H + d));
+    acc.x = fmaf(v, (m & 1u) ? w.x : 0.f, acc.x);
+    acc.y = fmaf(v, (m & 2u) ? w.y : 0.f, acc.y);
+    acc.z = fmaf(v, (m & 4u) ? w.z : 0.f, acc.z);
+    acc.w = fmaf(v, (m & 8u) ? w.w : 0.f, acc.w);
   }
+  const float sc = thr ? rscale : 1.0f;
+  float4* o = reinterpret_cast<float4*>(dcls + (int64_t)b * H + d);
+  float4 r = make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc);
+  if (accumulate) {
+    const float4 prev = *o;
+    r.x += prev.x;
+    r.y += prev.y;
+    r.z += prev.z;
+    r.w += prev.w;
+  }
+  *o = r;
 }
 
 __global__ void cls_scatter_kernel(const float* __restrict__ dcls, const int32_t* __restrict__ cu,
@@ -502,7 +521,8 @@ extern "C" int nbest_stc_head_bwd(nbest_ctx* ctx, const float* dlogits, const fl
   const float rscale = 1.0f / (1.0f - p_drop);
   stc_head_wgrad_kernel<<<dim3(h.n_cols, kWgradSplits), 192, 0, s>>>(dlogits, cls, B, h, thr, rscale, seed, dW, dbias);
   NBEST_CHECK_LAUNCH(ctx);
-  stc_head_dgrad_kernel<<<B, 256, 0, s>>>(dlogits, W, B, h, thr, rscale, seed, dcls, accumulate_dcls);
+  NBEST_CHECK_ARG(ctx, h.n_groups + 1 <= 16, "at most 15 multi-way value groups (4 keep bits per group in one word)");
+  stc_head_dgrad_kernel<<<B, 192, 0, s>>>(dlogits, W, B, h, thr, rscale, seed, dcls, accumulate_dcls);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
