@@ -108,7 +108,10 @@ typedef enum {
   NBEST_EPI_BIAS_DROP_RES = 3, /* C = dropout(acc + bias[n]; p_drop, seed) + aux[m,n]                 */
   NBEST_EPI_DGELU = 4,       /* C = acc * gelu_erf'(aux[m,n])                                         */
   NBEST_EPI_ADD = 5,         /* C = acc + aux[m,n]                                                    */
-  NBEST_EPI_ACCUM_F32 = 6    /* C (fp32) += acc     (wgrad; atomic accumulation, split-K)             */
+  NBEST_EPI_ACCUM_F32 = 6,   /* C (fp32) += acc     (wgrad; atomic accumulation, split-K)             */
+  NBEST_EPI_DELTA = 7        /* C = acc; out2 (fp32 [N/64][M]) = per-64-column dot(acc[m,:], aux[m,:]): the
+                              * attention backward's delta = rowsum(dO * O) per head, produced by the out-projection
+                              * dgrad that computes dO (flash-attention backward preprocess, fused)             */
 } nbest_epilogue;
 
 int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
@@ -128,6 +131,8 @@ int nbest_attn_varlen_fwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* c
  * T is the forward's token count (stride of lse / delta_ws and part of the dropout index); the B sequences given
  * here cover the first T_active <= T tokens (the gradient-carrying prefix: the ASR stream when the transcript
  * stream is forward-only, n_best_asr_bert.py:166). */
+/* out_bf16 may be NULL: delta_ws then already holds delta = rowsum(dO * O) per head with row pitch T_active (written by
+ * the out-projection dgrad GEMM with NBEST_EPI_DELTA) and the internal preprocess kernel is skipped. */
 int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens, const uint8_t* key_valid,
                           int B, int max_len, int heads, int T, int T_active, const void* out_bf16, const void* dout_bf16,
                           const float* lse, void* dqkv_bf16, float* delta_ws, float p_drop, uint32_t seed,

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
                      const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
                      const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                     float scale, uint32_t thr, float rscale, uint32_t seed) {
+                     float scale, uint32_t thr, float rscale, uint32_t seed, int dpitch) {
   const int kb = blockIdx.x, h0 = blockIdx.y * HPC, b = blockIdx.z;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   const int k0 = kb * BLK;
@@ -320,7 +320,7 @@ attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __res
     if (threadIdx.x < BLK) {
       const int q = q0 + threadIdx.x;
       sm.lse[st][threadIdx.x] = q < L ? lse[(int64_t)h * T + s0 + q] * kLog2e : INFINITY;   // +inf -> P = 0 (padded query)
-      sm.delta[st][threadIdx.x] = q < L ? delta[(int64_t)h * T + s0 + q] : 0.f;
+      sm.delta[st][threadIdx.x] = q < L ? delta[(int64_t)h * dpitch + s0 + q] : 0.f;
     }
     cp_async_commit();
   };
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
                    const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                   float scale, uint32_t thr, float rscale, uint32_t seed) {
+                   float scale, uint32_t thr, float rscale, uint32_t seed, int dpitch) {
   const int qb = blockIdx.x, h0 = blockIdx.y * HPC, b = blockIdx.z;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   const int q0 = qb * BLK;
@@ -433,7 +433,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restr
       if (threadIdx.x >= BLK) {
         const int i = threadIdx.x - BLK, q = q0 + i;
         sm.lse[hs][i] = q < L ? lse[(int64_t)h * T + s0 + q] * kLog2e : INFINITY;
-        sm.delta[hs][i] = q < L ? delta[(int64_t)h * T + s0 + q] : 0.f;
+        sm.delta[hs][i] = q < L ? delta[(int64_t)h * dpitch + s0 + q] : 0.f;
       }
     }
     load_tile(smem_u32(sm.k[st]), qkv + (int64_t)(s0 + k0) * ld + hd + h * D, ld, L - k0);
@@ -565,7 +565,7 @@ extern "C" int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const
                                      const void* out_bf16, const void* dout_bf16, const float* lse, void* dqkv_bf16,
                                      float* delta_ws, float p_drop, uint32_t seed, void* stream) {
   if (!ctx) return NBEST_EINVAL;
-  NBEST_CHECK_ARG(ctx, qkv_bf16 && cu_seqlens && out_bf16 && dout_bf16 && lse && dqkv_bf16 && delta_ws, "null pointer");
+  NBEST_CHECK_ARG(ctx, qkv_bf16 && cu_seqlens && dout_bf16 && lse && dqkv_bf16 && delta_ws, "null pointer");
   NBEST_CHECK_ARG(ctx, B > 0 && heads > 0 && max_len > 0 && max_len <= 512, "need 0 < max_len <= 512 (BERT position limit)");
   NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
   NBEST_CHECK_ARG(ctx, B <= 65535, "B too large for one launch");
@@ -575,7 +575,10 @@ extern "C" int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const
   const auto* o = reinterpret_cast<const __nv_bfloat16*>(out_bf16);
   const auto* g = reinterpret_cast<const __nv_bfloat16*>(dout_bf16);
   auto* dq = reinterpret_cast<__nv_bfloat16*>(dqkv_bf16);
-  if (T_active > 0) {
+  // out == NULL: delta_ws already holds delta = rowsum(dO * O) per head with row pitch T_active (written by the
+  // out-projection dgrad GEMM, NBEST_EPI_DELTA); otherwise it is computed here with row pitch T
+  const int dpitch = o ? T : T_active;
+  if (T_active > 0 && o) {
     attn_delta_kernel<<<(T_active + 7) / 8, 256, 0, s>>>(o, g, T_active, T, heads, delta_ws);
     NBEST_CHECK_LAUNCH(ctx);
   }
@@ -594,18 +597,18 @@ extern "C" int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const
   if (heads % 4 == 0) {
     const dim3 grid(nb, heads / 4, B);
     attn_bwd_dkdv_kernel<4><<<grid, kThreads, sizeof(DkdvSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq,
-                                                                    0.125f, thr, rscale, seed);
+                                                                    0.125f, thr, rscale, seed, dpitch);
     NBEST_CHECK_LAUNCH(ctx);
     attn_bwd_dq_kernel<4><<<grid, kThreads, sizeof(DqSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f,
-                                                                thr, rscale, seed);
+                                                                thr, rscale, seed, dpitch);
     NBEST_CHECK_LAUNCH(ctx);
   } else {
     const dim3 grid(nb, heads, B);
     attn_bwd_dkdv_kernel<1><<<grid, kThreads, sizeof(DkdvSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq,
-                                                                    0.125f, thr, rscale, seed);
+                                                                    0.125f, thr, rscale, seed, dpitch);
     NBEST_CHECK_LAUNCH(ctx);
     attn_bwd_dq_kernel<1><<<grid, kThreads, sizeof(DqSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f,
-                                                                thr, rscale, seed);
+                                                                thr, rscale, seed, dpitch);
     NBEST_CHECK_LAUNCH(ctx);
   }
   return NBEST_OK;

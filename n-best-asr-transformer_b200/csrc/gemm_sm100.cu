@@ -235,7 +235,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n0 = (tile % g.num_n_tiles) * BN;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int row = m0 + q * 32 + lane;  // the accumulator row this thread owns
-      constexpr bool kHasAux = (EPI == NBEST_EPI_BIAS_DROP_RES || EPI == NBEST_EPI_DGELU || EPI == NBEST_EPI_ADD);
+      constexpr bool kHasAux = (EPI == NBEST_EPI_BIAS_DROP_RES || EPI == NBEST_EPI_DGELU || EPI == NBEST_EPI_ADD ||
+                                EPI == NBEST_EPI_DELTA);
       const int crow = lane >> 2, cseg = lane & 3;   // coalesced aux loads: 8 rows x 64 B per warp instruction
       uint4 aux_next[4];
       auto load_aux = [&](int c) {
@@ -289,6 +290,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (EPI == NBEST_EPI_BIAS_GELU && pass == 0 && g.out2 == nullptr) continue;
             if (lane == 0) bulk_wait_read();   // the previous store from this buffer has finished reading it
             __syncwarp();
+            float dsum = 0.f;                  // EPI_DELTA: dot(acc, aux) over this 64-column unit (= one attention head)
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
               const int c = 2 * u + cc;
@@ -362,12 +364,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   v[2 * j] += bf16lo(auxrow[j]);
                   v[2 * j + 1] += bf16hi(auxrow[j]);
                 }
+              } else if constexpr (EPI == NBEST_EPI_DELTA) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  dsum = fmaf(v[2 * j], bf16lo(auxrow[j]), dsum);
+                  dsum = fmaf(v[2 * j + 1], bf16hi(auxrow[j]), dsum);
+                }
               }
 #pragma unroll
               for (int s4 = 0; s4 < 4; ++s4)
                 *reinterpret_cast<uint4*>(st + unit_off(lane, cc * 4 + s4)) =
                     make_uint4(pack_bf16x2(v[8 * s4], v[8 * s4 + 1]), pack_bf16x2(v[8 * s4 + 2], v[8 * s4 + 3]),
                                pack_bf16x2(v[8 * s4 + 4], v[8 * s4 + 5]), pack_bf16x2(v[8 * s4 + 6], v[8 * s4 + 7]));
+            }
+            if constexpr (EPI == NBEST_EPI_DELTA) {
+              if (row < g.M) reinterpret_cast<float*>(g.out2)[(int64_t)((n0 >> 6) + u) * g.M + row] = dsum;
             }
             fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
             __syncwarp();
@@ -458,6 +469,7 @@ int dispatch(nbest_ctx* ctx, int a_mn, int b_mn, int epi, const CUtensorMap& tmA
       case NBEST_EPI_NONE: return launch<BN, CG, false, true, NBEST_EPI_NONE>(ctx, tmA, tmB, tmC, tmC2, g, s);
       case NBEST_EPI_DGELU: return launch<BN, CG, false, true, NBEST_EPI_DGELU>(ctx, tmA, tmB, tmC, tmC2, g, s);
       case NBEST_EPI_ADD: return launch<BN, CG, false, true, NBEST_EPI_ADD>(ctx, tmA, tmB, tmC, tmC2, g, s);
+      case NBEST_EPI_DELTA: return launch<BN, CG, false, true, NBEST_EPI_DELTA>(ctx, tmA, tmB, tmC, tmC2, g, s);
       default: break;
     }
   } else if (a_mn && b_mn) {
@@ -483,7 +495,9 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
   NBEST_CHECK_ARG(ctx, ldc % 8 == 0, "ldc must be a multiple of 8");
   const bool needs_bias =
       epilogue == NBEST_EPI_BIAS || epilogue == NBEST_EPI_BIAS_GELU || epilogue == NBEST_EPI_BIAS_DROP_RES;
-  const bool needs_aux = epilogue == NBEST_EPI_BIAS_DROP_RES || epilogue == NBEST_EPI_DGELU || epilogue == NBEST_EPI_ADD;
+  const bool needs_aux = epilogue == NBEST_EPI_BIAS_DROP_RES || epilogue == NBEST_EPI_DGELU || epilogue == NBEST_EPI_ADD ||
+                         epilogue == NBEST_EPI_DELTA;
+  NBEST_CHECK_ARG(ctx, epilogue != NBEST_EPI_DELTA || out2_bf16, "NBEST_EPI_DELTA needs out2 (fp32 [N/64][M])");
   NBEST_CHECK_ARG(ctx, !needs_bias || bias, "epilogue needs bias");
   NBEST_CHECK_ARG(ctx, !needs_aux || (aux_bf16 && ldaux % 8 == 0), "epilogue needs aux with ldaux % 8 == 0");
   NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");

@@ -408,7 +408,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
         cu = pk.cu_seqlens[:B_act + 1]
         max_len = pk.max_len_asr if B_act == pk.B_asr and B_act != pk.B else pk.max_len
         dqkv = bf(T_act, 3 * H)
-        delta = torch.empty((s.heads, T), device=dev, dtype=torch.float32)
+        delta = torch.empty((s.heads, T_act), device=dev, dtype=torch.float32)     # written by the out-proj dgrad (EPI_DELTA)
         A = lambda t: t[:T_act]
         ws = {}       # per-row-count workspaces of the post-attention block: {n: (dpre, dprem, du, dx1, dctx)}
         for l in reversed(range(s.layers)):
@@ -432,7 +432,10 @@ class TOD_ASR_Transformer_STC(nn.Module):
             ops.ln_bwd(dx1, R(L.pre1), L.mean1, L.rstd1, w["p_g1"], dpre, w["g_g1"], w["g_b1"], dx_masked=dprem,
                        dbias=w["g_bo"], p_drop=p_h, seed=self._seed(l, 2), T=n)
             dm = dprem if p_h > 0 else dpre
-            ops.gemm(dm, w["h_wo"], b_mn_major=True, epilogue=ops.EPI_NONE, out=dctx)
+            if compact:
+                ops.gemm(dm, w["h_wo"], b_mn_major=True, epilogue=ops.EPI_NONE, out=dctx)
+            else:      # dO = dm Wo, and in the same epilogue the attention backward's delta = rowsum(dO * O) per head
+                ops.gemm(dm, w["h_wo"], b_mn_major=True, epilogue=ops.EPI_DELTA, aux=R(L.ctx), out=dctx, out2=delta[:, :n])
             ops.gemm(dm, R(L.ctx), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_wo"])
             # a window of short, non-persistent kernels (attention backward): the data-parallel trainer starts the pending
             # gradient all-reduces here, so that they run next to kernels that shrink gracefully instead of next to the
@@ -445,7 +448,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
                 dres.index_copy_(0, cu[:B_act].long(), dpre)
                 dx = bf(T_act, H)
             else:
-                ops.attn_bwd(L.qkv, cu, kv, B_act, max_len, s.heads, T, L.ctx, dctx, L.lse, dqkv, delta, p_a, self._seed(l, 1),
+                ops.attn_bwd(L.qkv, cu, kv, B_act, max_len, s.heads, T, None, dctx, L.lse, dqkv, delta, p_a, self._seed(l, 1),
                              T_active=T_act)
                 dres = dpre
             ops.gemm(dqkv, w["h_wqkv"], b_mn_major=True, epilogue=ops.EPI_ADD, aux=dres, out=dx)   # (full path: dx was consumed above)

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (EPI_ACCUM_F32, EPI_ADD, EPI_BIAS, EPI_BIAS_DROP_RES, EPI_BIAS_GELU, EPI_DGELU, EPI_NONE,  # noqa: F401
+from ._lib import (EPI_ACCUM_F32, EPI_ADD, EPI_BIAS, EPI_BIAS_DROP_RES, EPI_BIAS_GELU, EPI_DELTA, EPI_DGELU, EPI_NONE,  # noqa: F401
                    AdamTensor, Hierarchy)
 
 

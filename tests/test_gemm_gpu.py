@@ -112,3 +112,21 @@ def test_gemm_rejects_bad_shapes():
     a, w = _mk((64, 64)), _mk((100, 64))
     with pytest.raises(NbestError):
         ops.gemm(a, w)
+
+
+@pytest.mark.parametrize("M", [200, 1000, 12167])
+def test_gemm_dgrad_with_fused_attention_delta(M):
+    """NBEST_EPI_DELTA: C = dy W (dgrad, B MN-major) and, per 64-column unit (= attention head), delta[h, m] =
+    sum_c C[m, 64h + c] * O[m, 64h + c] — the flash-attention backward preprocess fused into the out-projection dgrad."""
+    from nbest_b200 import ops
+    N, K = 768, 768
+    dy = _mk((M, K), 1.0, 1)
+    w = _mk((K, N), 0.05, 2)                      # [K, N] row-major = MN-major B
+    o = _mk((M, N), 1.0, 3)
+    delta = torch.full((N // 64, M), float("nan"), device="cuda")
+    out = ops.gemm(dy, w, b_mn_major=True, epilogue=ops.EPI_DELTA, aux=o, out2=delta)
+    ref = dy.float() @ w.float()
+    assert _rel(out, ref) < 1e-2
+    ref_delta = (ref * o.float()).view(M, N // 64, 64).sum(-1).t()
+    assert torch.isfinite(delta).all()
+    assert _rel(delta, ref_delta) < 5e-3

@@ -271,6 +271,11 @@ def test_attention_fwd_bwd(lens):
     ops.attn_bwd(qkv, cu_d, key_valid, B, max(lens), heads, T, out, dout, lse, dqkv, delta)
     assert _rel(dqkv, ref_grads) < 2e-2
     assert _cos(dqkv, ref_grads) > 0.9995
+    # out = None: delta = rowsum(dO * O) per head is supplied by the caller (pitch T_active), e.g. by the EPI_DELTA GEMM
+    delta_in = (dout.float() * out.float()).view(T, heads, 64).sum(-1).t().contiguous()
+    dqkv2 = torch.empty_like(qkv)
+    ops.attn_bwd(qkv, cu_d, key_valid, B, max(lens), heads, T, None, dout, lse, dqkv2, delta_in)
+    assert _rel(dqkv2, dqkv) < 2e-3
     # key_valid = None means all keys valid
     ops.attn_fwd(qkv, cu_d, None, B, max(lens), heads, T, out, lse)
     ref2, _ = _attn_ref(qkv, cu, torch.ones_like(key_valid), heads)
