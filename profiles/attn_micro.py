@@ -3,10 +3,9 @@ import json, os, sys, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nbest_b200 import ops
 from nbest_b200.synth import synth_batch
-from oracle import stc_oracle as O   # hierarchy only (label tables for the generator)
 
 hj = json.load(open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "dstc2_hierarchy.json")))
-hier = O.Hierarchy({int(k): v for k, v in hj["top2bottom"].items()}, hj["none_bottoms"])
+hier = ops.DeviceHierarchy({int(k): v for k, v in hj["top2bottom"].items()}, hj["none_bottoms"], device="cuda")
 hyps = int(os.environ.get("HYPS", "5")); max_len = int(os.environ.get("MAXLEN", "128")); Bq = int(os.environ.get("BATCH", "256"))
 b = synth_batch("bert", 30522, hier, B=Bq, n_hyps=hyps, max_len=max_len, seed=999)
 la = (b["ids"] > 0).sum(1).numpy(); lt = (b["trans_ids"] > 0).sum(1).numpy()
