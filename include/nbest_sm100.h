@@ -106,7 +106,8 @@ typedef enum {
   NBEST_EPI_BIAS = 1,        /* C = acc + bias[n]                                                     */
   NBEST_EPI_BIAS_GELU = 2,   /* out2 = acc + bias (if out2 != NULL); C = gelu_erf(acc + bias)         */
   NBEST_EPI_BIAS_DROP_RES = 3, /* C = dropout(acc + bias[n]; p_drop, seed) + aux[m,n]                 */
-  NBEST_EPI_DGELU = 4,       /* C = acc * gelu_erf'(aux[m,n])                                         */
+  NBEST_EPI_DGELU = 4,       /* C = acc * gelu_erf'(aux[m,n]); if out2 != NULL: out2 (fp32 [N]) += sum_m C[m,n]
+                              * (the bias gradient of the layer that produced aux, fused)              */
   NBEST_EPI_ADD = 5,         /* C = acc + aux[m,n]                                                    */
   NBEST_EPI_ACCUM_F32 = 6,   /* C (fp32) += acc     (wgrad; atomic accumulation, split-K)             */
   NBEST_EPI_DELTA = 7        /* C = acc; out2 (fp32 [N/64][M]) = per-64-column dot(acc[m,:], aux[m,:]): the

@@ -386,6 +386,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_store_2d((EPI == NBEST_EPI_BIAS_GELU && pass == 0) ? &tmC2 : &tmC, st, n0 + u * 64, m0 + q * 32);
               bulk_commit();
             }
+            if constexpr (EPI == NBEST_EPI_DGELU) {
+              // optional fused bias gradient: out2[n] += sum_m C[m, n]. Lane j sums column pair (2j, 2j+1) of the staged
+              // 32 x 64 unit (the bf16 values the store writes; rows beyond M are exact zeros) and adds it to the fp32
+              // accumulator: one pass over du less than a separate column-sum kernel.
+              if (g.out2 != nullptr) {
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                  const uint32_t w2 = *reinterpret_cast<const uint32_t*>(st + unit_off(r, lane >> 2) + (lane & 3) * 4);
+                  s0 += bf16lo(w2);
+                  s1 += bf16hi(w2);
+                }
+                float* dst = reinterpret_cast<float*>(g.out2) + n0 + u * 64 + 2 * lane;
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(s0), "f"(s1) : "memory");
+              }
+            }
           }
         }
       }

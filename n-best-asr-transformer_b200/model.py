@@ -423,11 +423,11 @@ class TOD_ASR_Transformer_STC(nn.Module):
             ops.ln_bwd(dx, R(L.pre2), L.mean2, L.rstd2, w["p_g2"], dpre, w["g_g2"], w["g_b2"], dx_masked=dprem,
                        dbias=w["g_b2o"], p_drop=p_h, seed=self._seed(l, 3), T=n)
             dm = dprem if p_h > 0 else dpre
-            ops.gemm(dm, w["h_w2"], b_mn_major=True, epilogue=ops.EPI_DGELU, aux=R(L.u), out=du)           # du = (dm W2) * gelu'(u)
+            # du = (dm W2) * gelu'(u), and in the same epilogue the FFN-in bias gradient g_bi += column sums of du
+            ops.gemm(dm, w["h_w2"], b_mn_major=True, epilogue=ops.EPI_DGELU, aux=R(L.u), out=du, out2=w["g_bi"])
             ops.gemm(dm, R(L.g), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_w2"])
             ops.gemm(du, w["h_w1"], b_mn_major=True, epilogue=ops.EPI_ADD, aux=dpre, out=dx1)              # + residual grad
             ops.gemm(du, R(L.x1), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_w1"])
-            ops.colsum(du, w["g_bi"], T=n)
             # ---- attention block
             ops.ln_bwd(dx1, R(L.pre1), L.mean1, L.rstd1, w["p_g1"], dpre, w["g_g1"], w["g_b1"], dx_masked=dprem,
                        dbias=w["g_bo"], p_drop=p_h, seed=self._seed(l, 2), T=n)

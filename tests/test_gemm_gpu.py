@@ -130,3 +130,20 @@ def test_gemm_dgrad_with_fused_attention_delta(M):
     ref_delta = (ref * o.float()).view(M, N // 64, 64).sum(-1).t()
     assert torch.isfinite(delta).all()
     assert _rel(delta, ref_delta) < 5e-3
+
+
+@pytest.mark.parametrize("M", [130, 1000, 12167])
+def test_gemm_dgelu_with_fused_bias_gradient(M):
+    """NBEST_EPI_DGELU with out2: C = (dy W) * gelu'(u) and out2[n] += sum_m C[m, n] (accumulating, fp32)."""
+    from nbest_b200 import ops
+    N, K = 3072, 768
+    dy = _mk((M, K), 1.0, 4)
+    w = _mk((K, N), 0.05, 5)
+    u = _mk((M, N), 1.5, 6)
+    acc = torch.full((N,), 0.25, device="cuda")
+    out = ops.gemm(dy, w, b_mn_major=True, epilogue=ops.EPI_DGELU, aux=u, out2=acc)
+    ref = (dy.float() @ w.float()) * _dgelu(u.float())
+    assert _rel(out, ref) < 1.5e-2
+    assert _rel(acc - 0.25, out.float().sum(0)) < 2e-3          # exactly the column sums of what was stored (bf16)
+    out_b = ops.gemm(dy, w, b_mn_major=True, epilogue=ops.EPI_DGELU, aux=u)      # without out2: unchanged result
+    assert torch.equal(out, out_b)
