@@ -104,9 +104,11 @@ int nbest_cast_f32_bf16(nbest_ctx* ctx, const float* src, void* dst_bf16, int64_
 typedef enum {
   NBEST_EPI_NONE = 0,        /* C = acc                                                    (bf16 out) */
   NBEST_EPI_BIAS = 1,        /* C = acc + bias[n]                                                     */
-  NBEST_EPI_BIAS_GELU = 2,   /* out2 = acc + bias (if out2 != NULL); C = gelu_erf(acc + bias)         */
+  NBEST_EPI_BIAS_GELU = 2,   /* u = acc + bias; C = gelu_erf(u); out2 = gelu_erf'(u) (if out2 != NULL): the
+                              * derivative is saved instead of u, so that the backward epilogue is one multiply */
   NBEST_EPI_BIAS_DROP_RES = 3, /* C = dropout(acc + bias[n]; p_drop, seed) + aux[m,n]                 */
-  NBEST_EPI_DGELU = 4,       /* C = acc * gelu_erf'(aux[m,n]); if out2 != NULL: out2 (fp32 [N]) += sum_m C[m,n]
+  NBEST_EPI_DGELU = 4,       /* C = acc * aux[m,n], aux = gelu_erf'(u) saved by NBEST_EPI_BIAS_GELU; if out2 != NULL:
+                              * out2 (fp32 [N]) += sum_m C[m,n]
                               * (the bias gradient of the layer that produced aux, fused)              */
   NBEST_EPI_ADD = 5,         /* C = acc + aux[m,n]                                                    */
   NBEST_EPI_ACCUM_F32 = 6,   /* C (fp32) += acc     (wgrad; atomic accumulation, split-K)             */

@@ -56,16 +56,18 @@ struct GemmArgs {
   uint32_t seed;
 };
 
-template <int BN, int CG>
+template <int BN, int CG, bool kTwoOutputs = false>
 struct Cfg {
   static constexpr uint32_t kABytes = BM * BK * 2;               // per CTA: its own 128 rows of A
   static constexpr uint32_t kBBytes = (BN / CG) * BK * 2;        // per CTA: BN / CG rows of B
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (CG == 2) ? ((BN == 256) ? 6 : 8) : ((BN == 256) ? 4 : 6);   // 192 KiB of operand ring
-  // per epilogue warp: one 32-row x 128-byte store unit. (Two alternating units per warp, with wait_group.read 1, were
-  // measured: no gain — the epilogues are not waiting for the store engine — and they cost a pipeline stage.)
-  static constexpr uint32_t kStagingBytes = kEpiWarps * 4096;
+  // per epilogue warp: one 32-row x 128-byte store unit — two for the GELU epilogue, which produces gelu(u) and gelu'(u)
+  // from ONE pass over the accumulator and stores both. (Two alternating units for single-output epilogues were measured:
+  // no gain, the epilogues are not waiting for the store engine.)
+  static constexpr uint32_t kStagingPerWarp = kTwoOutputs ? 8192 : 4096;
+  static constexpr uint32_t kStagingBytes = kEpiWarps * kStagingPerWarp;
   static constexpr uint32_t kBiasBytes = 2 * BN * 4;   // the tile's bias slice, double buffered by tile parity
+  static constexpr int kStages = (232448 - 256 - kBiasBytes - kStagingBytes) / kStageBytes;   // fill the 227 KiB window
   static constexpr uint32_t kBarOffset = kStages * kStageBytes + kStagingBytes + kBiasBytes;
   static constexpr uint32_t kSmemBytes = kBarOffset + 256;   // + barriers; the dynamic window itself is 1024-byte aligned
   static constexpr uint32_t kTmemCols = 2 * BN;
@@ -79,7 +81,7 @@ template <int BN, int CG, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmArgs g) {
-  using C_ = Cfg<BN, CG>;
+  using C_ = Cfg<BN, CG, EPI == NBEST_EPI_BIAS_GELU>;
   constexpr int kStages = C_::kStages;
   // SWIZZLE_128B operand tiles need 1024-byte alignment; the window starts at the same offset in both CTAs of a pair
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -222,7 +224,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // is clipped by the tensor map. (Per-lane 16-byte st.global of 64-byte row segments cost 17 % of the GEMM.)
     const int q = warp & 3;
     const int u_first = warp >> 2;
-    uint8_t* st = staging + warp * 4096;
+    uint8_t* st = staging + warp * C_::kStagingPerWarp;
     float* bias_tile = reinterpret_cast<float*>(staging + C_::kStagingBytes);
     constexpr bool kHasBias = (EPI == NBEST_EPI_BIAS || EPI == NBEST_EPI_BIAS_GELU || EPI == NBEST_EPI_BIAS_DROP_RES);
     auto unit_off = [](int row, int chunk16) { return row * 128 + ((chunk16 ^ (row & 7)) << 4); };
@@ -284,10 +286,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll 1
         for (int u = u_first; u < BN / 64; u += 2) {
           if (g.debug == 1) break;
-          constexpr int kPasses = (EPI == NBEST_EPI_BIAS_GELU) ? 2 : 1;   // GELU: pass 0 stores u = acc + bias, pass 1 gelu(u)
-#pragma unroll 1
-          for (int pass = 0; pass < kPasses; ++pass) {
-            if (EPI == NBEST_EPI_BIAS_GELU && pass == 0 && g.out2 == nullptr) continue;
+          {
+            // GELU with out2: gelu(u) -> unit 0 of the staging buffer, gelu'(u) -> unit 1, both from this one pass
+            const bool both = (EPI == NBEST_EPI_BIAS_GELU) && g.out2 != nullptr;
             if (lane == 0) bulk_wait_read();   // the previous store from this buffer has finished reading it
             __syncwarp();
             float dsum = 0.f;                  // EPI_DELTA: dot(acc, aux) over this 64-column unit (= one attention head)
@@ -330,7 +331,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
               }
               if constexpr (EPI == NBEST_EPI_BIAS_GELU) {
-                if (pass == 1) {
+                if (both) {
+#pragma unroll
+                  for (int s4 = 0; s4 < 4; ++s4) {
+                    float d[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) gelu_fwd_grad(v[8 * s4 + j], v[8 * s4 + j], d[j]);
+                    *reinterpret_cast<uint4*>(st + 4096 + unit_off(lane, cc * 4 + s4)) =
+                        make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
+                  }
+                } else {
 #pragma unroll
                   for (int j = 0; j < 32; ++j) v[j] = gelu_fwd(v[j]);
                 }
@@ -354,9 +364,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
               } else if constexpr (EPI == NBEST_EPI_DGELU) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  v[2 * j] *= gelu_grad(bf16lo(auxrow[j]));
-                  v[2 * j + 1] *= gelu_grad(bf16hi(auxrow[j]));
+                for (int j = 0; j < 16; ++j) {   // aux = gelu'(u), saved by the forward's NBEST_EPI_BIAS_GELU epilogue
+                  v[2 * j] *= bf16lo(auxrow[j]);
+                  v[2 * j + 1] *= bf16hi(auxrow[j]);
                 }
               } else if constexpr (EPI == NBEST_EPI_ADD) {
 #pragma unroll
@@ -383,7 +393,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
             __syncwarp();
             if (lane == 0 && g.debug != 2) {
-              tma_store_2d((EPI == NBEST_EPI_BIAS_GELU && pass == 0) ? &tmC2 : &tmC, st, n0 + u * 64, m0 + q * 32);
+              tma_store_2d(&tmC, st, n0 + u * 64, m0 + q * 32);
+              if (both) tma_store_2d(&tmC2, st + 4096, n0 + u * 64, m0 + q * 32);
               bulk_commit();
             }
             if constexpr (EPI == NBEST_EPI_DGELU) {
@@ -431,7 +442,7 @@ template <int BN, int CG, bool A_MN, bool B_MN, int EPI>
 int launch(nbest_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
            const GemmArgs& g, cudaStream_t stream) {
   auto kfn = gemm_kernel<BN, CG, A_MN, B_MN, EPI>;
-  using C_ = Cfg<BN, CG>;
+  using C_ = Cfg<BN, CG, EPI == NBEST_EPI_BIAS_GELU>;
   static int max_units = 0;  // per instantiation: CTAs (CG = 1) or co-resident CTA pairs (CG = 2)
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
@@ -556,8 +567,11 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
     g.num_splits = want;
   }
   g.debug = getenv("NBEST_GEMM_DEBUG") ? atoi(getenv("NBEST_GEMM_DEBUG")) : 0;
-  g.stages = (CG == 2) ? ((BN == 256) ? Cfg<256, 2>::kStages : Cfg<128, 2>::kStages)
-                       : ((BN == 256) ? Cfg<256, 1>::kStages : Cfg<128, 1>::kStages);
+  const bool two = epilogue == NBEST_EPI_BIAS_GELU;
+  g.stages = (CG == 2) ? ((BN == 256) ? (two ? Cfg<256, 2, true>::kStages : Cfg<256, 2>::kStages)
+                                      : (two ? Cfg<128, 2, true>::kStages : Cfg<128, 2>::kStages))
+                       : ((BN == 256) ? (two ? Cfg<256, 1, true>::kStages : Cfg<256, 1>::kStages)
+                                      : (two ? Cfg<128, 1, true>::kStages : Cfg<128, 1>::kStages));
   if (const char* st = getenv("NBEST_GEMM_STAGES")) {
     const int v = atoi(st);
     if (v >= 1 && v < g.stages) g.stages = v;

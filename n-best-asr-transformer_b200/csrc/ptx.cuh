@@ -297,6 +297,16 @@ __device__ __forceinline__ float gelu_fwd(float z) {
   gelu_tail(z, w, e);
   return fmaf(-fabsf(z) * w, e, fmaxf(z, 0.f));
 }
+// both at once (shared polynomial / exponential): g = z Phi(z), d = Phi(z) + z phi(z)       (17 instructions, 2 MUFU)
+__device__ __forceinline__ void gelu_fwd_grad(float z, float& g, float& d) {
+  float w, e;
+  gelu_tail(z, w, e);
+  const float a = fabsf(z);
+  g = fmaf(-a * w, e, fmaxf(z, 0.f));
+  const float dd = fmaf(0.39894228040143268f, a, -w);
+  const float ds = __uint_as_float(__float_as_uint(dd) ^ (__float_as_uint(z) & 0x80000000u));
+  d = fmaf(ds, e, __float_as_int(z) >= 0 ? 1.0f : 0.f);
+}
 // Phi(z) + z phi(z) = step(z) + sign(z) e (|z|/sqrt(2 pi) - w)
 __device__ __forceinline__ float gelu_grad(float z) {
   float w, e;

@@ -365,6 +365,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
                      seed=self._seed(l, 2))
             L.mean1, L.rstd1 = f32(n), f32(n)
             ops.ln_fwd(pre1, w["p_g1"], w["p_b1"], s.ln_eps, x1, L.mean1, L.rstd1)
+            # gact = gelu(x1 W1 + b); u = gelu'(x1 W1 + b) — the derivative is saved, so the backward epilogue only multiplies
             ops.gemm(x1, w["h_w1"], epilogue=ops.EPI_BIAS_GELU, bias=w["p_bi"], out=gact, out2=u)
             ops.gemm(gact, w["h_w2"], epilogue=ops.EPI_BIAS_DROP_RES, bias=w["p_b2o"], aux=x1, out=pre2, p_drop=p_h,
                      seed=self._seed(l, 3))

@@ -45,10 +45,13 @@ def test_gemm_nt_gelu_two_outputs():
     a, w = _mk((M, K), 1.0, 3), _mk((N, K), 0.04, 4)
     bias = torch.randn(N, device="cuda") * 0.1
     u_ref = a.float() @ w.float().t() + bias
-    u = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
-    g = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU, bias=bias, out2=u)
-    assert _rel(u, u_ref) < 1e-2
+    d = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    g = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU, bias=bias, out2=d)
+    # out2 = gelu'(u): the derivative (not u) is what the forward saves for the backward's multiply-only epilogue
+    assert _rel(d, _dgelu(u_ref)) < 1e-2
     assert _rel(g, _gelu(u_ref)) < 1e-2
+    g_only = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU, bias=bias)          # inference: no second output
+    assert torch.equal(g, g_only)
     # gelu computed from the unrounded accumulator must match torch's exact-erf gelu tightly at small magnitudes too
     assert (g.float() - _gelu(u_ref)).abs().max().item() < 2e-2
 
@@ -87,9 +90,9 @@ def test_gemm_dgrad_b_mn_major(M, N, K):
     assert _rel(out, ref) < 1e-2
     out = ops.gemm(dy, w, b_mn_major=True, epilogue=ops.EPI_ADD, aux=r)
     assert _rel(out, ref + r.float()) < 1e-2
-    u = _mk((M, N), 1.5, 11)
-    out = ops.gemm(dy, w, b_mn_major=True, epilogue=ops.EPI_DGELU, aux=u)
-    assert _rel(out, ref * _dgelu(u.float())) < 1e-2
+    d = _dgelu(_mk((M, N), 1.5, 11).float()).to(torch.bfloat16)            # what EPI_BIAS_GELU saved in the forward
+    out = ops.gemm(dy, w, b_mn_major=True, epilogue=ops.EPI_DGELU, aux=d)
+    assert _rel(out, ref * d.float()) < 1e-2
 
 
 @pytest.mark.parametrize("T,NO,KI", [(64, 128, 128), (512, 128, 256), (1000, 768, 768), (3001, 3072, 768),
@@ -134,15 +137,15 @@ def test_gemm_dgrad_with_fused_attention_delta(M):
 
 @pytest.mark.parametrize("M", [130, 1000, 12167])
 def test_gemm_dgelu_with_fused_bias_gradient(M):
-    """NBEST_EPI_DGELU with out2: C = (dy W) * gelu'(u) and out2[n] += sum_m C[m, n] (accumulating, fp32)."""
+    """NBEST_EPI_DGELU with out2: C = (dy W) * aux (aux = gelu'(u)) and out2[n] += sum_m C[m, n] (accumulating, fp32)."""
     from nbest_b200 import ops
     N, K = 3072, 768
     dy = _mk((M, K), 1.0, 4)
     w = _mk((K, N), 0.05, 5)
-    u = _mk((M, N), 1.5, 6)
+    u = _dgelu(_mk((M, N), 1.5, 6).float()).to(torch.bfloat16)
     acc = torch.full((N,), 0.25, device="cuda")
     out = ops.gemm(dy, w, b_mn_major=True, epilogue=ops.EPI_DGELU, aux=u, out2=acc)
-    ref = (dy.float() @ w.float()) * _dgelu(u.float())
+    ref = (dy.float() @ w.float()) * u.float()
     assert _rel(out, ref) < 1.5e-2
     assert _rel(acc - 0.25, out.float().sum(0)) < 2e-3          # exactly the column sums of what was stored (bf16)
     out_b = ops.gemm(dy, w, b_mn_major=True, epilogue=ops.EPI_DGELU, aux=u)      # without out2: unchanged result
