@@ -170,3 +170,35 @@ def test_dropout_hash_restatement_is_a_sound_bernoulli_source():
     assert abs(float((a * b).mean())) / 0.09 < 5e-3
     gaps = np.diff(np.nonzero(O.dropout_keep_mask(3, 1 << 21, 0.1) == 0)[0])
     assert abs(gaps.mean() - 10.0) < 0.1 and abs(gaps.var() - 90.0) < 3.0
+
+
+def test_trainer_launches_every_bucket_once_at_the_announced_slots():
+    """DataParallelTrainer._grad_ready (host logic, no GPU): with collective slots a finished bucket waits for the next
+    'slot' the backward announces (or for 'emb', the last notification) and is launched exactly once, in completion order;
+    without slots it is launched immediately; names that are not buckets ('head', layers inside a merged bucket) are ignored."""
+    from nbest_b200.trainer import DataParallelTrainer
+    events = ["head"]
+    for l in reversed(range(4)):
+        events += ["slot", "layer%d" % l]
+    events.append("emb")
+
+    def run(slots, buckets):
+        t = object.__new__(DataParallelTrainer)
+        t.comm_slots, t._pending, t._bucket_names, launched = slots, [], set(buckets), []
+        t._launch_bucket = lambda name: launched.append((name, len(seen)))
+        seen = []
+        for e in events:
+            seen.append(e)
+            t._grad_ready(e)
+        return launched
+
+    one = ["layer3", "layer2", "layer1", "layer0", "emb"]
+    got = run(True, one)
+    assert [n for n, _ in got] == one
+    # layer3's bucket starts at the slot announced before layer2's backward window, ..., layer0 and emb at the very end
+    pos = {n: i for n, i in got}
+    assert events[pos["layer3"] - 1] == "slot" and events[pos["layer1"] - 1] == "slot" and pos["layer0"] == pos["emb"] == len(events)
+    got = run(False, one)
+    assert [n for n, _ in got if n in one] == one and all(events[i - 1] == n for n, i in got)      # immediately
+    two = ["layer2", "layer0", "emb"]                                  # two layers per bucket: named after the last to finish
+    assert [n for n, _ in run(True, two)] == two
