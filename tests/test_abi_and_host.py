@@ -202,3 +202,25 @@ def test_trainer_launches_every_bucket_once_at_the_announced_slots():
     assert [n for n, _ in got if n in one] == one and all(events[i - 1] == n for n, i in got)      # immediately
     two = ["layer2", "layer0", "emb"]                                  # two layers per bucket: named after the last to finish
     assert [n for n, _ in run(True, two)] == two
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU port of the reference step on the host cores) prints exactly one JSON line with
+    the contract's keys; it is the one bench leg that runs without a GPU."""
+    import json
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "utterances/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == dict(value=d["value"], unit=d["unit"], h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    assert "workload" in d["config"] and "model" not in d["config"]
