@@ -542,7 +542,8 @@ extern "C" int nbest_attn_varlen_fwd(nbest_ctx* ctx, const void* qkv_bf16, const
   const uint32_t thr = drop_threshold(p_drop);
   const float rscale = 1.0f / (1.0f - p_drop);
   const int nqb = (max_len + BLK - 1) / BLK;
-  static bool attr = false;
+  static bool attr_dev[64] = {};   // per device: cudaFuncSetAttribute applies to the current device only
+  bool& attr = attr_dev[ctx->device & 63];
   if (!attr) {
     int rc = set_smem(ctx, attn_fwd_kernel<4>, sizeof(FwdSmem));
     if (rc) return rc;
@@ -582,7 +583,8 @@ extern "C" int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const
     attn_delta_kernel<<<(T_active + 7) / 8, 256, 0, s>>>(o, g, T_active, T, heads, delta_ws);
     NBEST_CHECK_LAUNCH(ctx);
   }
-  static bool attr = false;
+  static bool attr_dev[64] = {};   // per device: cudaFuncSetAttribute applies to the current device only
+  bool& attr = attr_dev[ctx->device & 63];
   if (!attr) {
     int rc = set_smem(ctx, attn_bwd_dkdv_kernel<4>, sizeof(DkdvSmem));
     if (!rc) rc = set_smem(ctx, attn_bwd_dkdv_kernel<1>, sizeof(DkdvSmem));

@@ -624,7 +624,8 @@ extern "C" int nbest_ln_bwd(nbest_ctx* ctx, const void* dy_bf16, const void* x_b
   if (T <= 0) return NBEST_OK;
   int blocks = (T + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (blocks > ctx->num_sms) blocks = ctx->num_sms;   // one block per SM (register-bound); fewer blocks = fewer column atomics
-  static bool attr = false;
+  static bool attr_dev[64] = {};   // per device: cudaFuncSetAttribute applies to the current device only
+  bool& attr = attr_dev[ctx->device & 63];
   if (!attr) {
     NBEST_CHECK_CUDA(ctx, cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnBwdSmem));
     attr = true;

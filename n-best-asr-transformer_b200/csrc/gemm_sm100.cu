@@ -443,7 +443,8 @@ int launch(nbest_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const
            const GemmArgs& g, cudaStream_t stream) {
   auto kfn = gemm_kernel<BN, CG, A_MN, B_MN, EPI>;
   using C_ = Cfg<BN, CG, EPI == NBEST_EPI_BIAS_GELU>;
-  static int max_units = 0;  // per instantiation: CTAs (CG = 1) or co-resident CTA pairs (CG = 2)
+  static int max_units_dev[64] = {};  // per instantiation and device: CTAs (CG = 1) or co-resident CTA pairs (CG = 2)
+  int& max_units = max_units_dev[ctx->device & 63];
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   cfg.blockDim = dim3(kThreads);
