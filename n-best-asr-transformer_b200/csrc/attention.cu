@@ -12,6 +12,8 @@
 //   forward : O, LSE
 //   backward: delta = rowsum(dO*O); dK,dV kernel (one CTA per key block, loops query blocks, S^T formulation);
 //             dQ kernel (one CTA per query block, loops key blocks). No atomics, no fp32 dQ buffer.
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -289,11 +291,11 @@ __global__ void __launch_bounds__(kThreads, 3)
 attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
                      const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
                      const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                     float scale, uint32_t thr, float rscale, uint32_t seed, int dpitch) {
+                     float scale, uint32_t thr, float rscale, uint32_t seed, int dpitch, int min_len) {
   const int kb = blockIdx.x, h0 = blockIdx.y * HPC, b = blockIdx.z;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   const int k0 = kb * BLK;
-  if (k0 >= L) return;
+  if (k0 >= L || L < min_len) return;   // min_len = 65: single-tile sequences belong to attn_bwd_fused_kernel
   extern __shared__ __align__(128) uint8_t smem_raw[];
   DkdvSmem& sm = *reinterpret_cast<DkdvSmem*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -411,11 +413,11 @@ __global__ void __launch_bounds__(kThreads, 3)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
                    const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                   float scale, uint32_t thr, float rscale, uint32_t seed, int dpitch) {
+                   float scale, uint32_t thr, float rscale, uint32_t seed, int dpitch, int min_len) {
   const int qb = blockIdx.x, h0 = blockIdx.y * HPC, b = blockIdx.z;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   const int q0 = qb * BLK;
-  if (q0 >= L) return;
+  if (q0 >= L || L < min_len) return;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   DqSmem& sm = *reinterpret_cast<DqSmem*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -515,6 +517,175 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, L <= 64
+// Sequences whose keys fit ONE 64-key tile (82 % of DSTC2 5-best sequences) need no block loops: one CTA per (sequence,
+// 4 heads) computes S and dP ONCE and derives dQ, dK and dV from them — 5 matrix products and one softmax / dropout pass
+// per head instead of the 9 products and two passes of the dK/dV + dQ kernel pair, and Q, K, V, dO are staged once.
+//   phase 1 (warp w = query rows 16w..):  S = Q K^T, dP = dO V^T, Pd = dropout(P), dS = P o (dropout'(dP) - delta);
+//            Pd and dS go to shared memory as bf16 [query][key] tiles;  dQ = dS K straight from the registers.
+//   phase 2 (warp w = key rows 16w..):    dV = Pd^T dO, dK = dS^T Q, the transposed A fragments come from ldmatrix.trans.
+// The next head's tiles are prefetched (cp.async) after the barrier that opens a head, so two barriers per head suffice.
+struct FusedSmem {
+  __nv_bfloat16 q[2][kTile], k[2][kTile], v[2][kTile], dO[2][kTile];   // stage = head parity
+  __nv_bfloat16 p[kTile], ds[kTile];
+};
+
+// A fragment (16 x 16) of the TRANSPOSE of a row-major [k][row] tile: A[row0 + i][16 kk + j] = tile[16 kk + j][row0 + i].
+__device__ __forceinline__ void lda_trans(uint32_t (&a)[4], uint32_t sbase, int row0, int kk, int lane) {
+  ldmatrix_x4_trans(a, tile_addr(sbase, kk * 16 + ((lane >> 4) << 3) + (lane & 7), (row0 >> 3) + ((lane >> 3) & 1)));
+}
+
+template <int HPC>
+__global__ void __launch_bounds__(kThreads, 2)
+attn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
+                      const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
+                      const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
+                      float scale, uint32_t thr, float rscale, uint32_t seed, int dpitch) {
+  const int h0 = blockIdx.x * HPC, b = blockIdx.y;
+  const int s0 = cu[b], L = cu[b + 1] - s0;
+  if (L <= 0 || L > BLK) return;               // longer sequences: attn_bwd_dkdv_kernel + attn_bwd_dq_kernel
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t ld = 3 * heads * D;
+  const int hd = heads * D;
+  const float sl2 = scale * kLog2e;
+  const int npairs = (L + 15) >> 4;            // 16-row groups (queries and keys alike) that hold real tokens
+  const bool warp_active = warp * 16 < L;
+  // validity of this thread's 16 key columns (c = 8 nt + 2 (lane & 3) + i), bit 2 nt + i
+  uint32_t vbits = 0;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = nt * 8 + (lane & 3) * 2 + i;
+      const bool ok = c < L && (key_valid == nullptr || key_valid[s0 + (c < L ? c : 0)] != 0);
+      vbits |= (ok ? 1u : 0u) << (2 * nt + i);
+    }
+  const uint32_t uP = smem_u32(sm.p), uS = smem_u32(sm.ds);
+
+  auto issue = [&](int hl) {
+    const int st = hl & 1, h = h0 + hl;
+    load_tile(smem_u32(sm.q[st]), qkv + (int64_t)s0 * ld + h * D, ld, L);
+    load_tile(smem_u32(sm.k[st]), qkv + (int64_t)s0 * ld + hd + h * D, ld, L);
+    load_tile(smem_u32(sm.v[st]), qkv + (int64_t)s0 * ld + 2 * hd + h * D, ld, L);
+    load_tile(smem_u32(sm.dO[st]), dout + (int64_t)s0 * hd + h * D, hd, L);
+    cp_async_commit();
+  };
+
+  issue(0);
+  for (int hl = 0; hl < HPC; ++hl) {
+    const int st = hl & 1, h = h0 + hl;
+    cp_async_wait<0>();
+    __syncthreads();          // this head's tiles are visible; every warp has left the previous head (P / dS tiles, other stage)
+    if (hl + 1 < HPC) issue(hl + 1);
+    const uint32_t uQ = smem_u32(sm.q[st]), uK = smem_u32(sm.k[st]), uV = smem_u32(sm.v[st]), uO = smem_u32(sm.dO[st]);
+    if (warp_active) {
+      // ---- phase 1: rows = queries 16 warp ..
+      float lse2[2], dl[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int qrow = warp * 16 + (lane >> 2) + 8 * r;
+        lse2[r] = qrow < L ? lse[(int64_t)h * T + s0 + qrow] * kLog2e : INFINITY;     // +inf -> P = 0 (padded query)
+        dl[r] = qrow < L ? delta[(int64_t)h * dpitch + s0 + qrow] : 0.f;
+      }
+      float s[8][4], dp[8][4];
+      zero_acc(s);
+      zero_acc(dp);
+      mma_a_tile_b_nk(s, uQ, warp * 16, uK, lane, npairs);      // S  [16 q x 64 keys]
+      mma_a_tile_b_nk(dp, uO, warp * 16, uV, lane, npairs);     // dP [16 q x 64 keys] = dO V^T
+#pragma unroll
+      for (int np = 0; np < 4; ++np)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          if (np >= npairs) continue;
+          uint2 hh = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+          if (thr) {
+            const int tq = s0 + warp * 16 + (lane >> 2) + 8 * r;
+            hh = dropout_quad(seed, attn_quad_row(h, T, tq) + (uint32_t)(np << 2) + (lane & 3));
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {                   // keys 16 np + 2 (lane & 3) + {0, 1, 8, 9}
+            const int nt = 2 * np + (i >> 1), e = 2 * r + (i & 1);
+            const bool valid = (vbits >> (2 * nt + (i & 1))) & 1u;
+            const float pr = valid ? ex2_approx(s[nt][e] * sl2 - lse2[r]) : 0.f;
+            float d = dp[nt][e], pd = pr;
+            if (thr) {
+              const uint32_t w = (i & 2) ? hh.y : hh.x;
+              const bool keep = ((i & 1) ? (w >> 16) : (w & 0xFFFFu)) >= thr;
+              pd = keep ? pr * rscale : 0.f;
+              d = keep ? d * rscale : 0.f;
+            }
+            s[nt][e] = pd;                                // dropped P -> dV
+            dp[nt][e] = pr * (d - dl[r]);                 // dS        -> dQ, dK
+          }
+        }
+      // Pd and dS as bf16 [query][key] tiles for phase 2
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        if (nt >= 2 * npairs) break;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int row = warp * 16 + (lane >> 2) + 8 * r;
+          const uint32_t off = (uint32_t)(row * 128 + ((nt ^ (row & 7)) << 4) + (lane & 3) * 4);
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(sm.p) + off) = pack_bf16x2(s[nt][2 * r], s[nt][2 * r + 1]);
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(sm.ds) + off) = pack_bf16x2(dp[nt][2 * r], dp[nt][2 * r + 1]);
+        }
+      }
+      float dq[8][4];
+      zero_acc(dq);
+      mma_p_b_kn(dq, dp, uK, lane, npairs);               // dQ = dS K   (B = K [key][d])
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int row = warp * 16 + (lane >> 2) + 8 * r;
+        if (row < L) {
+          __nv_bfloat16* qrow = dqkv + (int64_t)(s0 + row) * ld + h * D + (lane & 3) * 2;
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt)
+            *reinterpret_cast<uint32_t*>(qrow + nt * 8) = pack_bf16x2(dq[nt][2 * r] * scale, dq[nt][2 * r + 1] * scale);
+        }
+      }
+    }
+    __syncthreads();          // the P / dS tiles are complete
+    if (warp_active) {
+      // ---- phase 2: rows = keys 16 warp ..
+      float dk[8][4], dv[8][4];
+      zero_acc(dk);
+      zero_acc(dv);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (kk >= npairs) break;
+        uint32_t ap[4], as[4];
+        lda_trans(ap, uP, warp * 16, kk, lane);           // Pd^T [16 keys x 16 queries]
+        lda_trans(as, uS, warp * 16, kk, lane);           // dS^T
+#pragma unroll
+        for (int dpn = 0; dpn < 4; ++dpn) {
+          uint32_t bo[4], bq[4];
+          ldb_kn(bo, uO, kk * 16, dpn * 2, lane);         // dO [q][d]
+          ldb_kn(bq, uQ, kk * 16, dpn * 2, lane);         // Q  [q][d]
+          mma_bf16_16816(dv[2 * dpn], ap, bo[0], bo[1]);
+          mma_bf16_16816(dv[2 * dpn + 1], ap, bo[2], bo[3]);
+          mma_bf16_16816(dk[2 * dpn], as, bq[0], bq[1]);
+          mma_bf16_16816(dk[2 * dpn + 1], as, bq[2], bq[3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int row = warp * 16 + (lane >> 2) + 8 * r;
+        if (row < L) {
+          __nv_bfloat16* krow = dqkv + (int64_t)(s0 + row) * ld + hd + h * D + (lane & 3) * 2;
+          __nv_bfloat16* vrow = krow + hd;
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            *reinterpret_cast<uint32_t*>(krow + nt * 8) = pack_bf16x2(dk[nt][2 * r] * scale, dk[nt][2 * r + 1] * scale);
+            *reinterpret_cast<uint32_t*>(vrow + nt * 8) = pack_bf16x2(dv[nt][2 * r], dv[nt][2 * r + 1]);
+          }
+        }
+      }
+    }
+  }
+}
+
 inline uint32_t drop_threshold(float p) {
   const double t = (double)p * 65536.0 + 0.5;   // 16-bit threshold (ptx.cuh dropout_keep)
   return p <= 0.f ? 0u : (t >= 65535.0 ? 65535u : (uint32_t)t);
@@ -596,21 +767,39 @@ extern "C" int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const
   const int nb = (max_len + BLK - 1) / BLK;
   const uint32_t thr = drop_threshold(p_drop);
   const float rscale = 1.0f / (1.0f - p_drop);
-  if (heads % 4 == 0) {
+  // sequences of <= 64 tokens: the fused single-tile kernel; longer ones: the dK/dV + dQ pair (skipped when there are none)
+  const bool use_fused = heads % 4 == 0 && getenv("NBEST_ATTN_NO_FUSED_BWD") == nullptr;
+  int min_len = 0;
+  if (use_fused) {
+    static bool fattr_dev[64] = {};
+    if (!fattr_dev[ctx->device & 63]) {
+      int rc = set_smem(ctx, attn_bwd_fused_kernel<4>, sizeof(FusedSmem));
+      if (rc) return rc;
+      fattr_dev[ctx->device & 63] = true;
+    }
+    attn_bwd_fused_kernel<4><<<dim3(heads / 4, B), kThreads, sizeof(FusedSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse,
+                                                                                   delta_ws, dq, 0.125f, thr, rscale, seed, dpitch);
+    NBEST_CHECK_LAUNCH(ctx);
+    if (max_len <= BLK) return NBEST_OK;
+    min_len = BLK + 1;
+  }
+  // (with the fused kernel in front only the few long sequences are left: one head per CTA gives them 4x more, 4x
+  //  shorter CTAs — with 4 heads per CTA the leftover grid is less than a wave and runs at one CTA's serial latency)
+  if (heads % 4 == 0 && !use_fused) {
     const dim3 grid(nb, heads / 4, B);
     attn_bwd_dkdv_kernel<4><<<grid, kThreads, sizeof(DkdvSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq,
-                                                                    0.125f, thr, rscale, seed, dpitch);
+                                                                    0.125f, thr, rscale, seed, dpitch, min_len);
     NBEST_CHECK_LAUNCH(ctx);
     attn_bwd_dq_kernel<4><<<grid, kThreads, sizeof(DqSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f,
-                                                                thr, rscale, seed, dpitch);
+                                                                thr, rscale, seed, dpitch, min_len);
     NBEST_CHECK_LAUNCH(ctx);
   } else {
     const dim3 grid(nb, heads, B);
     attn_bwd_dkdv_kernel<1><<<grid, kThreads, sizeof(DkdvSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq,
-                                                                    0.125f, thr, rscale, seed, dpitch);
+                                                                    0.125f, thr, rscale, seed, dpitch, min_len);
     NBEST_CHECK_LAUNCH(ctx);
     attn_bwd_dq_kernel<1><<<grid, kThreads, sizeof(DqSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f,
-                                                                thr, rscale, seed, dpitch);
+                                                                thr, rscale, seed, dpitch, min_len);
     NBEST_CHECK_LAUNCH(ctx);
   }
   return NBEST_OK;
