@@ -205,5 +205,5 @@ def test_bucketed_adam_on_side_stream_equals_single_step_update():
     a, b = res
     cos = lambda x, y: float((x.double() @ y.double()) / (x.double().norm() * y.double().norm()))
     assert a[3] == b[3] and max(a[3]) == 4
-    assert cos(a[0], b[0]) > 1 - 1e-7 and cos(a[1], b[1]) > 0.999 and cos(a[2], b[2]) > 0.999
+    assert cos(a[0], b[0]) > 1 - 1e-6 and cos(a[1], b[1]) > 0.999 and cos(a[2], b[2]) > 0.999    # fp32 atomic order of wgrad
     assert torch.allclose(a[4], b[4], rtol=2e-3)
