@@ -4,6 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
+BASELINE.json configs -> flags (default = configs[1], the configuration the metric is quoted on):
+    configs[1]  (default)                                         BERT-base 5-best, max_len 128, B 256/GPU, training
+    configs[2]  --model xlmr                                      XLM-R-base (250 k vocab), data-parallel training
+    configs[3]  --l2                                              + transcript stream with gradients and the MSE term
+    configs[4]  --mode infer --hyps 10 --max-len 512 --batch 512  10-best inference (forward + decode), N replicas
+
 Workload (BASELINE.json configs[1]): BERT-base-uncased, 5-best hypotheses [SEP]-joined, max_len 128, batch 256 per GPU,
 synthetic DSTC2-shaped token ids (nbest_b200.synth), random-init weights, act-slot + value heads, both encoder streams as
 the reference runs them (transcript stream forward-only without --add_l2_loss), dropout on (0.1 / 0.1 / 0.3), BertAdam
@@ -15,7 +21,11 @@ with the reference's per-tensor groups. One "step" = one optimizer step over one
   roofline   dominant kernel = the tcgen05 GEMM (all instances of one step): algorithmic FLOPs / CUDA-event time of those
              launches, against the measured sustained bf16 peak in MEASURED_PEAKS.json
   cpu_baseline  the oracle port of the reference path timed on this box's host cores on a bounded sample (rank 0, N=1)
---impl reference times that CPU port alone (the reference is pure Python + PyTorch; its sources cannot travel to the box).
+  gpu_eager_baseline  (informational) the unmodified reference on the SAME B200 through stock PyTorch, fp32 as written and
+             with the HF encoder under autocast(bf16) (SURVEY §8(d) secondary baseline)
+--impl reference times THE REFERENCE ITSELF — the unmodified modules staged under oracle/_ref/ by oracle/vendor_ref.py
+(git-ignored, travels with the snapshot) — on the box's host cores, B = 32 per step, with the
+fwd / bwd / optimizer split. Only if nothing is staged does it fall back to the oracle port (kind "port").
 """
 import argparse
 import json
@@ -88,23 +98,83 @@ def cpu_port_step_time(n_utt, steps, warmup, seed=999, threads=None):
     return float(np.median(times)), float(np.sum(times)), threads
 
 
+def workload_name(args):
+    enc = "XLM-RoBERTa-base (250k vocab)" if args.model == "xlmr" else "BERT-base-uncased"
+    if args.mode == "infer":
+        return "%s %d-hypothesis n-best, max_len %d, batch %d/GPU inference (forward + decode), bf16 packed varlen" % (
+            enc, args.hyps, args.max_len, args.batch)
+    return "%s n-best STC bf16 packed varlen, batch %d/GPU, %d hyps, max_len %d%s%s" % (
+        enc, args.batch, args.hyps, args.max_len, ", dense" if args.dense else "", ", add_l2_loss" if args.l2 else "")
+
+
+def metric_name(args):
+    enc = "XLM-R-base" if args.model == "xlmr" else "BERT-base"
+    if args.mode == "infer":
+        return "inference utterances/s (fwd+decode) %s n-best STC" % enc
+    return "train utterances/s (fwd+bwd+step) %s n-best STC" % enc
+
+
+def reference_cpu(args, n_utt, steps, warmup):
+    """(utt/s, ms/step, cpu_baseline dict): the staged reference on the host cores, else the oracle port."""
+    from oracle import ref_loader
+    kind = "xlm-roberta" if args.model == "xlmr" else "bert"
+    if ref_loader.available():
+        from oracle import ref_bench
+        if args.mode == "infer":
+            r = ref_bench.time_infer("cpu", n_utt, steps, warmup, kind, args.hyps, args.max_len)
+            split = None
+        else:
+            r = ref_bench.time_train("cpu", n_utt, steps, warmup, kind, args.l2, args.hyps, args.max_len)
+            split = dict(fwd_ms=r["fwd_s"] * 1e3, bwd_ms=r["bwd_s"] * 1e3, optimizer_ms=r["opt_s"] * 1e3)
+        v = n_utt / r["median_s"]
+        cb = dict(value=v, unit=UNIT, cores=r["threads"], kind="reference",
+                  sample="the unmodified reference (oracle/_ref: make_model + cal_total_loss + backward + BertAdam, fp32, dropout "
+                         "on, both streams) on %d-utterance batches of the same generator, %d warm-up + %d timed steps, %.1f s" % (
+                             n_utt, warmup, steps, r["total_s"]), ms_per_step=r["median_s"] * 1e3)
+        if split:
+            cb["split"] = split
+        return v, r["median_s"] * 1e3, cb
+    med, total, threads = cpu_port_step_time(n_utt, steps, warmup)
+    v = n_utt / med
+    return v, med * 1e3, dict(value=v, unit=UNIT, cores=threads, kind="port", ms_per_step=med * 1e3,
+                              sample="oracle port (reference not staged), %d-utterance batches, %d timed steps" % (n_utt, steps))
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_utt = 16
-    med, total, threads = cpu_port_step_time(n_utt, args.steps, max(1, min(args.warmup, 2)))
-    v = n_utt / med
-    line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=med * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="BERT-base-uncased n-best STC bf16 packed varlen, batch %d/GPU, %d hyps, max_len %d" % (
-                    args.batch, args.hyps, args.max_len), global_batch=args.batch, parallelism="cpu",
-                    sample="each timed step = a %d-utterance slice of that workload (same generator, both streams, dropout on, "
-                           "fp32, BertAdam) on the host cores" % n_utt, device="cpu"),
-                cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind="port",
-                                  sample="%d-utterance batches of the same generator, %d timed steps" % (n_utt, args.steps)),
-                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    n_utt = 32 if args.mode == "train" else 16                     # BASELINE.md §3: batch 32 (configs[0])
+    v, ms, cb = reference_cpu(args, n_utt, args.steps, max(1, min(args.warmup, 2)))
+    line = dict(impl="reference", metric=metric_name(args), value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic",
+                config=dict(workload=workload_name(args), global_batch=args.batch, parallelism="cpu",
+                            sample="each timed step = a %d-utterance batch of that workload (same generator) on the host cores" % n_utt,
+                            device="cpu"),
+                cpu_baseline=cb, e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
+
+
+def gpu_eager_baseline(args, dev):
+    """The unmodified reference on the same GPU through stock PyTorch kernels (informational)."""
+    from oracle import ref_loader
+    if not ref_loader.available() or args.mode != "train":
+        return None
+    from oracle import ref_bench
+    kind = "xlm-roberta" if args.model == "xlmr" else "bert"
+    out = {}
+    for name, ac in (("fp32_as_written", False), ("encoder_autocast_bf16", True)):
+        try:
+            r = ref_bench.time_train(str(dev), args.batch, 3, 2, kind, args.l2, args.hyps, args.max_len, autocast_encoder=ac)
+            out[name] = dict(value=args.batch / r["median_s"], unit=UNIT, ms_per_step=r["median_s"] * 1e3,
+                             fwd_ms=r["fwd_s"] * 1e3, bwd_ms=r["bwd_s"] * 1e3, optimizer_ms=r["opt_s"] * 1e3)
+        except Exception as e:      # informational leg: never fails the bench
+            out[name] = dict(error=repr(e)[:200])
+        torch.cuda.empty_cache()
+    out["note"] = "reference code + HF encoder + torch %s kernels on this GPU, batch %d, padded, both streams, 221-group BertAdam" % (
+        torch.__version__, args.batch)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -162,7 +232,10 @@ def main():
     ap.add_argument("--max-len", type=int, default=128)
     ap.add_argument("--dense", action="store_true", help="every sequence exactly max_len tokens (roofline worst case)")
     ap.add_argument("--l2", action="store_true", help="--add_l2_loss: transcript stream with gradients + MSE term")
+    ap.add_argument("--model", default="bert", choices=["bert", "xlmr"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--skip-transcript", action="store_true",
                     help="do not run the transcript stream at all (without --add_l2_loss the reference computes it forward-only "
@@ -191,10 +264,13 @@ def main():
     hj = load_hierarchy()
     t2b = {int(k): v for k, v in hj["top2bottom"].items()}
     drop = 0.0 if args.no_dropout else None
-    spec = EncoderSpec.bert_base() if drop is None else EncoderSpec.bert_base(hidden_dropout=0.0, attn_dropout=0.0)
+    mk = EncoderSpec.xlmr_base if args.model == "xlmr" else EncoderSpec.bert_base
+    kind = "xlm-roberta" if args.model == "xlmr" else "bert"
+    spec = mk() if drop is None else mk(hidden_dropout=0.0, attn_dropout=0.0)
+    infer = args.mode == "infer"
     model = TOD_ASR_Transformer_STC(spec=spec, top2bottom=t2b, dropout=0.3 if drop is None else 0.0, device=dev,
                                     none_bottoms=hj["none_bottoms"], seed=999)
-    model.train()
+    model.train(not infer)
     groups = []
     for n, p in model.named_parameters():                          # reference n_best_asr_bert.py:535-550
         no_decay = any(nd in n for nd in ("bias", "LayerNorm.bias", "LayerNorm.weight"))
@@ -205,27 +281,55 @@ def main():
 
     # ---- synthetic batches: pinned host copies (e2e) + device-resident copies (value)
     NB = 4
-    host, devb, stats = [], [], []
+    host, devb, stats, len_max, tlen_max = [], [], [], [], []
     keys = ("ids", "seg", "trans_ids", "trans_seg", "labels")
     for i in range(NB):
-        b = synth_batch("bert", spec.vocab_size, model.hier, args.batch, args.hyps, args.max_len, seed=999 + 1000 * rank + i,
+        b = synth_batch(kind, spec.vocab_size, model.hier, args.batch, args.hyps, args.max_len, seed=999 + 1000 * rank + i,
                         dense=args.dense)
         host.append({k: b[k].pin_memory() for k in keys} | dict(lens=b["lens"], trans_lens=b["trans_lens"]))
         devb.append({k: b[k].to(dev) for k in keys} | dict(lens=b["lens"], trans_lens=b["trans_lens"]))
         L = np.array(b["lens"], dtype=np.float64)
         Lt = np.array(b["trans_lens"], dtype=np.float64)
         stats.append((L.sum(), (L ** 2).sum(), Lt.sum(), (Lt ** 2).sum()))
+        len_max.append(int(b["ids"].shape[1]))
+        tlen_max.append(int(b["trans_ids"].shape[1]))
     h2d_bytes = int(np.mean([sum(h[k].numel() * h[k].element_size() for k in keys) for h in host]))
 
     skip_t = args.skip_transcript and not args.l2
+    if infer:
+        from nbest_b200.epoch import EpochMetrics
+        keys = ("ids", "seg", "labels")
+        h2d_bytes = int(np.mean([sum(h[k].numel() * h[k].element_size() for k in keys) for h in host]))
+        metrics = EpochMetrics(dev)
+        dec_host = torch.empty((args.batch, model.hier.n_bottom), dtype=torch.uint8).pin_memory()
+
+    def infer_dev(i):
+        # eval_epoch's hot path (n_best_asr_bert.py:316-350) without the loss: forward, decode bitmap, device-side counters
+        b = devb[i % NB]
+        head = model.infer(b["ids"], b["seg"], b["lens"])
+        metrics.update(head.decode, b["labels"])
+        return head.decode
+
+    def infer_host(i):
+        h = host[i % NB]
+        d = {k: h[k].to(dev, non_blocking=True) for k in keys}
+        head = model.infer(d["ids"], d["seg"], h["lens"])
+        metrics.update(head.decode, d["labels"])
+        dec_host.copy_(head.decode, non_blocking=True)              # D2H of the step's result: the prediction bitmap
+        torch.cuda.current_stream().synchronize()
+        return dec_host
 
     def step_dev(i):
+        if infer:
+            return infer_dev(i)
         b = devb[i % NB]
         if skip_t:
             return trainer.step(b["ids"], b["labels"], None, b["seg"], None, b["lens"], None)
         return trainer.step(b["ids"], b["labels"], b["trans_ids"], b["seg"], b["trans_seg"], b["lens"], b["trans_lens"])
 
     def step_host(i):
+        if infer:
+            return infer_host(i)
         h = host[i % NB]
         d = {k: h[k].to(dev, non_blocking=True) for k in keys}
         if skip_t:
@@ -266,8 +370,9 @@ def main():
     for i in range(2):
         step_host(i)
     ms_e2e, _, last_losses = timed(step_host, args.steps)
-    if not bool(torch.isfinite(last_losses).all()):
+    if not infer and not bool(torch.isfinite(last_losses).all()):
         raise SystemExit("non-finite loss in the benchmark step")
+    d2h_bytes = int(dec_host.numel()) if infer else 16
 
     # ---- per-kernel roofline leg: two instrumented steps (CUDA events around every launch of ours)
     # (the per-bucket BertAdam normally runs on a side stream under the backward; the instrumented steps serialise it on
@@ -296,8 +401,15 @@ def main():
         value = utt / (ms / 1e3)
         T, L2, Tt, Lt2 = np.mean([s[0] for s in stats]), np.mean([s[1] for s in stats]), np.mean([s[2] for s in stats]), \
             np.mean([s[3] for s in stats])
-        alg = 3.0 * (GEMM_FLOPS_PER_TOKEN_FWD * T + ATTN_FLOPS_PER_L2_FWD * L2)                      # BASELINE.md formula (ASR stream)
-        alg_all = alg + (3.0 if args.l2 else 1.0) * (GEMM_FLOPS_PER_TOKEN_FWD * Tt + ATTN_FLOPS_PER_L2_FWD * Lt2)
+        if kind != "bert":          # the reference leaves <pad> attendable for XLM-R: every row is real work at the batch maximum
+            S_, St_ = np.asarray(len_max, dtype=np.float64), np.asarray(tlen_max, dtype=np.float64)
+            T, L2, Tt, Lt2 = args.batch * S_.mean(), args.batch * (S_ ** 2).mean(), args.batch * St_.mean(), args.batch * (St_ ** 2).mean()
+        if infer:
+            alg = alg_all = GEMM_FLOPS_PER_TOKEN_FWD * T + ATTN_FLOPS_PER_L2_FWD * L2
+            Tt = 0.0
+        else:
+            alg = 3.0 * (GEMM_FLOPS_PER_TOKEN_FWD * T + ATTN_FLOPS_PER_L2_FWD * L2)                  # BASELINE.md formula (ASR stream)
+            alg_all = alg + (3.0 if args.l2 else (0.0 if skip_t else 1.0)) * (GEMM_FLOPS_PER_TOKEN_FWD * Tt + ATTN_FLOPS_PER_L2_FWD * Lt2)
         step_s = ms / 1e3 / args.steps
         gemm_ms = sum(agg[k][0] for k in agg if k.startswith("gemm"))
         gemm_fl = sum(agg[k][1] for k in agg if k.startswith("gemm"))
@@ -306,32 +418,36 @@ def main():
                            tflops=round(v[1] / (v[0] * 1e-3) / 1e12, 1) if v[1] else None,
                            gbs=round(v[2] / (v[0] * 1e-3) / 1e9, 1) if v[2] else None) for k, v in sorted(agg.items())}
         line = dict(
-            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+            metric=metric_name(args), value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-            config=dict(workload="BERT-base-uncased n-best STC bf16 packed varlen, batch %d/GPU, %d hyps, max_len %d%s%s" % (
-                args.batch, args.hyps, args.max_len, ", dense" if args.dense else "", ", add_l2_loss" if args.l2 else ""),
+            config=dict(workload=workload_name(args),
                 global_batch=world * args.batch, tokens_per_step_asr=float(T), tokens_per_step_transcript=float(Tt),
-                parallelism="dp%d" % world, dropout="off" if args.no_dropout else "0.1/0.1/0.3",
-                streams="asr fwd+bwd, transcript %s" % ("fwd+bwd" if args.l2 else ("skipped (--skip-transcript)" if skip_t else
-                                                                                    "fwd only (as the reference)")),
-                l2_flush="per-step working set (activations + 438 MB fp32 weights + Adam state, > 4 GB) exceeds the 126 MB L2"),
+                parallelism=("replicas%d" if infer else "dp%d") % world,
+                dropout="off" if (args.no_dropout or infer) else "0.1/0.1/0.3",
+                streams="asr forward + decode (eval mode)" if infer else "asr fwd+bwd, transcript %s" % (
+                    "fwd+bwd" if args.l2 else ("skipped (--skip-transcript)" if skip_t else "fwd only (as the reference)")),
+                l2_flush="per-step working set (activations + fp32 weights%s, > 1 GB) exceeds the 126 MB L2" % (
+                    "" if infer else " + Adam state")),
             clocks=clocks,
-            e2e=dict(value=utt / (ms_e2e / 1e3), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=16,
+            e2e=dict(value=utt / (ms_e2e / 1e3), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
                      ms_per_step=ms_e2e / args.steps),
             gpu_launches=int(launches),
             roofline=dict(bound="tensor", kernel="gemm_kernel (tcgen05, all instances of one step)", achieved=achieved,
-                          peak=pk["tf_sustained"], unit="TFLOP/s", frac=achieved / pk["tf_sustained"], traffic=gemm_traffic() if (args.batch == 256 and args.hyps == 5 and not args.dense and not args.l2) else None,
+                          peak=pk["tf_sustained"], unit="TFLOP/s", frac=achieved / pk["tf_sustained"], traffic=gemm_traffic() if (args.batch == 256 and args.hyps == 5 and not args.dense and not args.l2 and not infer and
+                                                     args.model == "bert") else None,
                           peak_source=pk["src"] + " bf16_tflops_sustained", gemm_ms_per_step=gemm_ms,
                           gemm_share_of_step=gemm_ms / (step_s * 1e3)),
             tc_util=dict(asr_stream_formula=alg / (step_s * pk["tf_sustained"] * 1e12),
                          all_executed_streams=alg_all / (step_s * pk["tf_sustained"] * 1e12)),
             kernels=kernels)
+        if world == 1 and not args.no_eager_baseline:
+            del trainer, optim, devb
+            torch.cuda.empty_cache()
+            eb = gpu_eager_baseline(args, dev)
+            if eb is not None:
+                line["gpu_eager_baseline"] = eb
         if world == 1 and not args.no_cpu_baseline:
-            n_utt = 32
-            med, total, threads = cpu_port_step_time(n_utt, 2, 1)
-            line["cpu_baseline"] = dict(value=n_utt / med, unit=UNIT, cores=threads, kind="port",
-                                        sample="%d-utterance batch (BASELINE configs[0] shape), 1 warm-up + 2 timed steps, %.1f s" % (
-                                            n_utt, total), ms_per_step=med * 1e3)
+            _, _, line["cpu_baseline"] = reference_cpu(args, 32 if not infer else 16, 3 if not infer else 2, 1)
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NBEST_ABI_VERSION 1
+#define NBEST_ABI_VERSION 2
 
 typedef struct nbest_ctx nbest_ctx;
 
@@ -57,6 +57,13 @@ uint64_t nbest_launch_count(nbest_ctx* ctx);
 int nbest_pack_batch(nbest_ctx* ctx, const int64_t* ids, const int64_t* seg_ids, int B, int S, int pos_mode,
                      int32_t* lens, int32_t* cu_seqlens, int32_t* tokens, uint8_t* seg, int32_t* pos,
                      int32_t* seq_of, uint8_t* key_valid, void* stream);
+/* Hypothesis-id map of the packed layout (north_star (1): "segment/hypothesis-id map built on the GPU"). The n-best
+ * list is joined as `[CLS] sys [SEP] hyp1 [SEP] hyp2 ... hypN [SEP]` (utils/bert_xlnet_inputs.py:75-85); hyp_id[t] =
+ * number of separator tokens (sep_id: 102 for BERT, 2 for XLM-R) at earlier positions of t's sequence, i.e. 0 for
+ * [CLS] + system turn + the first [SEP], k for the tokens of hypothesis k and the [SEP] that closes it (saturates at
+ * 255). tokens / cu_seqlens are nbest_pack_batch outputs. */
+int nbest_pack_hyp_ids(nbest_ctx* ctx, const int32_t* tokens, const int32_t* cu_seqlens, int B, int sep_id,
+                       uint8_t* hyp_id, void* stream);
 
 /* ---- K1: embedding gather + LayerNorm (+dropout) ---------------------------------------------------------- */
 /* BertEmbeddings.forward (transformers/models/bert/modeling_bert.py:102-112), called from models/model.py:43-45.
@@ -231,6 +238,18 @@ int nbest_bertadam_step(nbest_ctx* ctx, float* p, const float* g, float* m, floa
                         const nbest_adam_tensor* tensors, int n_tensors, const int32_t* chunks, int n_chunks,
                         float* norms_ws, double sched, float b1, float b2, float eps, float max_grad_norm,
                         void* stream);
+
+/* The other two optimizers n_best_asr_bert.py:553-569 can select, over the same flat buffers and tensor table:
+ *   NBEST_ADAM_HF_ADAMW  transformers(2.3.0).AdamW(correct_bias=False) (:563): p -= lr m/(sqrt(v)+eps); p -= lr wd p
+ *   NBEST_ADAM_TORCH     torch.optim.Adam (:554): L2-coupled decay, bias correction with the 1-based `step`
+ * global_clip != 0 replaces BertAdam's per-tensor clipping by torch.nn.utils.clip_grad_norm_(all params, max_grad_norm)
+ * (n_best_asr_bert.py:268-271): one coefficient from the 2-norm over every active tensor. sched multiplies each
+ * tensor's lr (get_linear_schedule_with_warmup's lambda for AdamW, :564-568; 1 for Adam). */
+typedef enum { NBEST_ADAM_BERT = 0, NBEST_ADAM_HF_ADAMW = 1, NBEST_ADAM_TORCH = 2 } nbest_adam_mode;
+int nbest_adam_step(nbest_ctx* ctx, int mode, float* p, const float* g, float* m, float* v, void* p_bf16,
+                    const nbest_adam_tensor* tensors, int n_tensors, const int32_t* chunks, int n_chunks,
+                    float* norms_ws, double sched, float b1, float b2, float eps, float max_grad_norm, int global_clip,
+                    int step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libnbest_sm100.so")
 
 NBEST_OK = 0
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_DROP_RES, EPI_DGELU, EPI_ADD, EPI_ACCUM_F32, EPI_DELTA = range(8)
+ADAM_BERT, ADAM_HF_ADAMW, ADAM_TORCH = range(3)
 
 _vp, _i32, _i64, _u32, _u64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_double
 
@@ -32,6 +33,7 @@ _SIGNATURES = {
     "nbest_last_error": (C.c_char_p, [_vp]),
     "nbest_launch_count": (_u64, [_vp]),
     "nbest_pack_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nbest_pack_hyp_ids": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "nbest_embed_ln_fwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _f32, C.c_int, _vp, _vp, _vp,
                                      _f32, _u32, _vp]),
     "nbest_embed_ln_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _f32, _u32,
@@ -59,6 +61,8 @@ _SIGNATURES = {
     "nbest_stc_metrics": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "nbest_bertadam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _f64, _f32, _f32,
                                       _f32, _f32, _vp]),
+    "nbest_adam_step": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _f64, _f32, _f32,
+                                  _f32, _f32, C.c_int, C.c_int, _vp]),
 }
 
 _lib = None

@@ -29,9 +29,8 @@ def save_checkpoint(path, model, optimizer=None, cursor=None):
         flat.ensure_moments()
         ck["optimizer"] = dict(m=flat.m.detach().cpu(), v=flat.v.detach().cpu(), steps=list(optimizer._steps),
                                total=int(flat.total), offsets=list(flat.offsets),
-                               groups=[dict(lr=g["lr"], weight_decay=g["weight_decay"], warmup=g["warmup"], t_total=g["t_total"],
-                                            schedule=g["schedule"], b1=g["b1"], b2=g["b2"], e=g["e"],
-                                            max_grad_norm=g["max_grad_norm"]) for g in optimizer.param_groups])
+                               groups=[{k: (list(v) if isinstance(v, tuple) else v) for k, v in g.items() if k != "params"}
+                                       for g in optimizer.param_groups])
     tmp = path + ".tmp"
     torch.save(ck, tmp)
     os.replace(tmp, path)

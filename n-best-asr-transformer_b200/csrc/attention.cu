@@ -707,6 +707,8 @@ extern "C" int nbest_attn_varlen_fwd(nbest_ctx* ctx, const void* qkv_bf16, const
   NBEST_CHECK_ARG(ctx, B > 0 && heads > 0 && max_len > 0 && max_len <= 512, "need 0 < max_len <= 512 (BERT position limit)");
   NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
   NBEST_CHECK_ARG(ctx, B <= 65535, "B too large for one launch");
+  // attention-dropout counters are (head * T + query token) * 128 + key quad in 32 bits (ptx.cuh attn_quad_row)
+  NBEST_CHECK_ARG(ctx, p_drop <= 0.f || (int64_t)heads * (int64_t)T < (1LL << 25), "dropout counter (h * T + t) * 128 would wrap 32 bits");
   const auto* q = reinterpret_cast<const __nv_bfloat16*>(qkv_bf16);
   auto* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -742,6 +744,7 @@ extern "C" int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const
   NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
   NBEST_CHECK_ARG(ctx, B <= 65535, "B too large for one launch");
   NBEST_CHECK_ARG(ctx, T_active >= 0 && T_active <= T, "need 0 <= T_active <= T");
+  NBEST_CHECK_ARG(ctx, p_drop <= 0.f || (int64_t)heads * (int64_t)T < (1LL << 25), "dropout counter (h * T + t) * 128 would wrap 32 bits");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const auto* q = reinterpret_cast<const __nv_bfloat16*>(qkv_bf16);
   const auto* o = reinterpret_cast<const __nv_bfloat16*>(out_bf16);

@@ -6,6 +6,8 @@
 // correction. The reference launches ~14 kernels per tensor (~3 k per step); here it is two launches per step:
 //   pass 1: per-tensor sum of squares of the gradient                       (reads g:           4 B / param)
 //   pass 2: clip + moments + decay + update (+ bf16 working copy refresh)   (reads p,g,m,v, writes p,m,v[,bf16]: 28-30 B)
+#include <math.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -39,29 +41,56 @@ adam_norm_kernel(const float* __restrict__ g, const nbest_adam_tensor* __restric
   }
 }
 
-__device__ __forceinline__ float adam_elem(float& p, float g, float& m, float& v, float coef, float b1, float b2, float eps,
-                                           float wd, float lr_t) {
+// One element of the three optimizers n_best_asr_bert.py:553-569 can select (MODE = nbest_adam_mode):
+//   BERTADAM  models/optimization.py:275-293     u = m/(sqrt(v)+e) + wd p;  p -= lr_t u            (no bias correction)
+//   ADAMW_HF  transformers 2.3.0 optimization.py AdamW.step with correct_bias=False (n_best_asr_bert.py:563):
+//             p -= lr_t m/(sqrt(v)+e);  then  p -= lr_t wd p   (decoupled decay applied to the UPDATED parameter)
+//   ADAM      torch.optim.Adam (n_best_asr_bert.py:554): g += wd p (L2);  p -= (lr_t/bc1) m / (sqrt(v)/sqrt(bc2) + e)
+template <int MODE>
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float coef, float b1, float b2, float eps,
+                                          float wd, float lr_t, float inv_bc1, float inv_sqrt_bc2) {
   g *= coef;
+  if (MODE == NBEST_ADAM_TORCH && wd > 0.f) g += wd * p;
   m = m * b1 + (1.0f - b1) * g;
   v = v * b2 + (1.0f - b2) * g * g;
-  float upd = m / (sqrtf(v) + eps);
-  if (wd > 0.f) upd += wd * p;
-  p -= lr_t * upd;
-  return p;
+  if (MODE == NBEST_ADAM_BERT) {
+    float upd = m / (sqrtf(v) + eps);
+    if (wd > 0.f) upd += wd * p;
+    p -= lr_t * upd;
+  } else if (MODE == NBEST_ADAM_HF_ADAMW) {
+    p -= lr_t * (m / (sqrtf(v) + eps));
+    if (wd > 0.f) p -= lr_t * wd * p;
+  } else {
+    p -= (lr_t * inv_bc1) * (m / (sqrtf(v) * inv_sqrt_bc2 + eps));
+  }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                   __nv_bfloat16* __restrict__ pb, const nbest_adam_tensor* __restrict__ tensors,
+                   __nv_bfloat16* __restrict__ pb, const nbest_adam_tensor* __restrict__ tensors, int n_tensors,
                    const int32_t* __restrict__ chunks, const float* __restrict__ norms, double sched, float b1, float b2,
-                   float eps, float max_grad_norm) {
+                   float eps, float max_grad_norm, int global_clip, float inv_bc1, float inv_sqrt_bc2) {
   const int ti = chunks[3 * blockIdx.x], start = chunks[3 * blockIdx.x + 1], len = chunks[3 * blockIdx.x + 2];
   const nbest_adam_tensor t = tensors[ti];
   const int64_t base = t.offset + start;
   float coef = 1.0f;
   if (max_grad_norm > 0.f) {
-    const float nrm = sqrtf(norms[ti]);
-    coef = fminf(max_grad_norm / (nrm + 1e-6f), 1.0f);   // clip_grad_norm_: clamp(max_norm / (norm + 1e-6), max=1)
+    float sq = norms[ti];
+    if (global_clip) {
+      // torch.nn.utils.clip_grad_norm_ over ALL parameters (n_best_asr_bert.py:268-271): the 2-norm of the per-tensor
+      // norms; every block folds the <= few hundred partial sums itself (inactive tensors hold 0)
+      __shared__ float tot;
+      float a = 0.f;
+      for (int i = threadIdx.x; i < n_tensors; i += kThreads) a += norms[i];
+      a = warp_sum(a);
+      if (threadIdx.x == 0) tot = 0.f;
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) atomicAdd(&tot, a);
+      __syncthreads();
+      sq = tot;
+    }
+    coef = fminf(max_grad_norm / (sqrtf(sq) + 1e-6f), 1.0f);   // clip_grad_norm_: clamp(max_norm / (norm + 1e-6), max=1)
   }
   const float lr_t = (float)(t.lr * sched);
   const float wd = t.weight_decay;
@@ -71,10 +100,10 @@ adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
     const float4 gv = __ldg(reinterpret_cast<const float4*>(g + base) + i);
     float4 mv = reinterpret_cast<float4*>(m + base)[i];
     float4 vv = reinterpret_cast<float4*>(v + base)[i];
-    adam_elem(pv.x, gv.x, mv.x, vv.x, coef, b1, b2, eps, wd, lr_t);
-    adam_elem(pv.y, gv.y, mv.y, vv.y, coef, b1, b2, eps, wd, lr_t);
-    adam_elem(pv.z, gv.z, mv.z, vv.z, coef, b1, b2, eps, wd, lr_t);
-    adam_elem(pv.w, gv.w, mv.w, vv.w, coef, b1, b2, eps, wd, lr_t);
+    adam_elem<MODE>(pv.x, gv.x, mv.x, vv.x, coef, b1, b2, eps, wd, lr_t, inv_bc1, inv_sqrt_bc2);
+    adam_elem<MODE>(pv.y, gv.y, mv.y, vv.y, coef, b1, b2, eps, wd, lr_t, inv_bc1, inv_sqrt_bc2);
+    adam_elem<MODE>(pv.z, gv.z, mv.z, vv.z, coef, b1, b2, eps, wd, lr_t, inv_bc1, inv_sqrt_bc2);
+    adam_elem<MODE>(pv.w, gv.w, mv.w, vv.w, coef, b1, b2, eps, wd, lr_t, inv_bc1, inv_sqrt_bc2);
     reinterpret_cast<float4*>(p + base)[i] = pv;
     reinterpret_cast<float4*>(m + base)[i] = mv;
     reinterpret_cast<float4*>(v + base)[i] = vv;
@@ -82,7 +111,7 @@ adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
   }
   for (int i = (n4 << 2) + threadIdx.x; i < len; i += kThreads) {
     float pv = p[base + i], mv = m[base + i], vv = v[base + i];
-    adam_elem(pv, g[base + i], mv, vv, coef, b1, b2, eps, wd, lr_t);
+    adam_elem<MODE>(pv, g[base + i], mv, vv, coef, b1, b2, eps, wd, lr_t, inv_bc1, inv_sqrt_bc2);
     p[base + i] = pv;
     m[base + i] = mv;
     v[base + i] = vv;
@@ -92,13 +121,15 @@ adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
 
 }  // namespace
 
-extern "C" int nbest_bertadam_step(nbest_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16,
-                                   const nbest_adam_tensor* tensors, int n_tensors, const int32_t* chunks, int n_chunks,
-                                   float* norms_ws, double sched, float b1, float b2, float eps, float max_grad_norm,
-                                   void* stream) {
+extern "C" int nbest_adam_step(nbest_ctx* ctx, int mode, float* p, const float* g, float* m, float* v, void* p_bf16,
+                               const nbest_adam_tensor* tensors, int n_tensors, const int32_t* chunks, int n_chunks,
+                               float* norms_ws, double sched, float b1, float b2, float eps, float max_grad_norm,
+                               int global_clip, int step, void* stream) {
   if (!ctx) return NBEST_EINVAL;
   NBEST_CHECK_ARG(ctx, p && g && m && v && tensors && chunks && norms_ws, "null pointer");
   NBEST_CHECK_ARG(ctx, n_tensors > 0 && n_chunks > 0, "empty tensor table");
+  NBEST_CHECK_ARG(ctx, mode == NBEST_ADAM_BERT || mode == NBEST_ADAM_HF_ADAMW || mode == NBEST_ADAM_TORCH, "unknown mode");
+  NBEST_CHECK_ARG(ctx, mode != NBEST_ADAM_TORCH || step >= 1, "torch Adam needs the 1-based step count (bias correction)");
   NBEST_CHECK_ARG(ctx, ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                          reinterpret_cast<uintptr_t>(v)) & 15) == 0, "flat buffers must be 16-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -107,8 +138,30 @@ extern "C" int nbest_bertadam_step(nbest_ctx* ctx, float* p, const float* g, flo
     adam_norm_kernel<<<n_chunks, kThreads, 0, s>>>(g, tensors, chunks, norms_ws);
     NBEST_CHECK_LAUNCH(ctx);
   }
-  adam_update_kernel<<<n_chunks, kThreads, 0, s>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), tensors, chunks,
-                                                    norms_ws, sched, b1, b2, eps, max_grad_norm);
+  float inv_bc1 = 1.f, inv_sqrt_bc2 = 1.f;
+  if (mode == NBEST_ADAM_TORCH) {
+    inv_bc1 = (float)(1.0 / (1.0 - pow((double)b1, (double)step)));
+    inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, (double)step)));
+  }
+  auto* pb = reinterpret_cast<__nv_bfloat16*>(p_bf16);
+  if (mode == NBEST_ADAM_BERT)
+    adam_update_kernel<NBEST_ADAM_BERT><<<n_chunks, kThreads, 0, s>>>(p, g, m, v, pb, tensors, n_tensors, chunks, norms_ws, sched,
+                                                                       b1, b2, eps, max_grad_norm, global_clip, inv_bc1, inv_sqrt_bc2);
+  else if (mode == NBEST_ADAM_HF_ADAMW)
+    adam_update_kernel<NBEST_ADAM_HF_ADAMW><<<n_chunks, kThreads, 0, s>>>(p, g, m, v, pb, tensors, n_tensors, chunks, norms_ws,
+                                                                           sched, b1, b2, eps, max_grad_norm, global_clip, inv_bc1,
+                                                                           inv_sqrt_bc2);
+  else
+    adam_update_kernel<NBEST_ADAM_TORCH><<<n_chunks, kThreads, 0, s>>>(p, g, m, v, pb, tensors, n_tensors, chunks, norms_ws, sched,
+                                                                        b1, b2, eps, max_grad_norm, global_clip, inv_bc1, inv_sqrt_bc2);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
+}
+
+extern "C" int nbest_bertadam_step(nbest_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16,
+                                   const nbest_adam_tensor* tensors, int n_tensors, const int32_t* chunks, int n_chunks,
+                                   float* norms_ws, double sched, float b1, float b2, float eps, float max_grad_norm,
+                                   void* stream) {
+  return nbest_adam_step(ctx, NBEST_ADAM_BERT, p, g, m, v, p_bf16, tensors, n_tensors, chunks, n_chunks, norms_ws, sched, b1, b2,
+                         eps, max_grad_norm, 0, 0, stream);
 }

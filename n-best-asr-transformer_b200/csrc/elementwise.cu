@@ -97,6 +97,23 @@ __global__ void pack_scatter_kernel(const int64_t* __restrict__ ids, const int64
   }
 }
 
+// hyp_id[t] = number of separator tokens before position t of its sequence (one warp per sequence, ballot scan)
+__global__ void pack_hyp_ids_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ cu, int B, int sep_id,
+                                    uint8_t* __restrict__ hyp_id) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const int lane = threadIdx.x & 31;
+  const int t0 = cu[row], L = cu[row + 1] - cu[row];
+  int carry = 0;
+  for (int c = 0; c < L; c += 32) {
+    const int j = c + lane;
+    const bool is_sep = j < L && tokens[t0 + j] == sep_id;
+    const uint32_t m = __ballot_sync(0xffffffffu, is_sep);
+    if (j < L) hyp_id[t0 + j] = (uint8_t)min(255, carry + __popc(m & ((1u << lane) - 1u)));
+    carry += __popc(m);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm core
 struct RowStats {
   float mean, rstd;
@@ -554,6 +571,16 @@ extern "C" int nbest_pack_batch(nbest_ctx* ctx, const int64_t* ids, const int64_
   return NBEST_OK;
 }
 
+extern "C" int nbest_pack_hyp_ids(nbest_ctx* ctx, const int32_t* tokens, const int32_t* cu_seqlens, int B, int sep_id,
+                                  uint8_t* hyp_id, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, tokens && cu_seqlens && hyp_id, "null pointer");
+  NBEST_CHECK_ARG(ctx, B > 0, "empty batch");
+  pack_hyp_ids_kernel<<<(B + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tokens, cu_seqlens, B, sep_id, hyp_id);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
 extern "C" int nbest_embed_ln_fwd(nbest_ctx* ctx, const int32_t* tokens, const uint8_t* seg, const int32_t* pos, int T,
                                   const float* word, const float* posemb, const float* type, const float* gamma,
                                   const float* beta, float eps, int hidden, void* y_bf16, float* mean, float* rstd,
@@ -562,6 +589,7 @@ extern "C" int nbest_embed_ln_fwd(nbest_ctx* ctx, const int32_t* tokens, const u
   NBEST_CHECK_ARG(ctx, hidden == H, "hidden must be 768");
   NBEST_CHECK_ARG(ctx, tokens && seg && pos && word && posemb && type && gamma && beta && y_bf16 && mean && rstd, "null pointer");
   NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
+  NBEST_CHECK_ARG(ctx, p_drop <= 0.f || (int64_t)T * 768 < (1LL << 32), "dropout counter t * 768 + c would wrap 32 bits");
   if (T <= 0) return NBEST_OK;
   embed_ln_fwd_kernel<<<(T + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       tokens, seg, pos, T, word, posemb, type, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y_bf16), mean, rstd,
@@ -620,6 +648,7 @@ extern "C" int nbest_ln_bwd(nbest_ctx* ctx, const void* dy_bf16, const void* x_b
   NBEST_CHECK_ARG(ctx, hidden == H, "hidden must be 768");
   NBEST_CHECK_ARG(ctx, dy_bf16 && x_bf16 && mean && rstd && gamma && dx_bf16 && dgamma && dbeta, "null pointer");
   NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
+  NBEST_CHECK_ARG(ctx, p_drop <= 0.f || (int64_t)T * 768 < (1LL << 32), "dropout counter t * 768 + c would wrap 32 bits");
   NBEST_CHECK_ARG(ctx, !(p_drop > 0.f) || dx_masked_bf16, "p_drop > 0 needs dx_masked");
   if (T <= 0) return NBEST_OK;
   int blocks = (T + kWarpsPerBlock - 1) / kWarpsPerBlock;

@@ -529,6 +529,9 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
   NBEST_CHECK_ARG(ctx, !needs_bias || bias, "epilogue needs bias");
   NBEST_CHECK_ARG(ctx, !needs_aux || (aux_bf16 && ldaux % 8 == 0), "epilogue needs aux with ldaux % 8 == 0");
   NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
+  // the dropout mask of element (row, col) is keyed on the 32-bit counter row * N + col (ptx.cuh dropout_keep4)
+  NBEST_CHECK_ARG(ctx, !(epilogue == NBEST_EPI_BIAS_DROP_RES && p_drop > 0.f) || (int64_t)M * (int64_t)N < (1LL << 32),
+                  "dropout counter row * N + col would wrap 32 bits (M * N >= 2^32)");
 
   // CTA pairs (256 x BN tiles, tcgen05.mma.cta_group::2) unless NBEST_GEMM_CTA_GROUP=1 asks for the single-CTA kernel.
   int CG = 2;

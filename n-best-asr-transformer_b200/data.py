@@ -38,6 +38,39 @@ def read_wcn_lines(path):
     return asr, trans, labels
 
 
+def stratified_sample(asr_seqs, trans_seqs, label_lists, coverage, seed=42):
+    """The reference's `--coverage` sampler (`_get_stratified_sampled_data`, utils/dataset/tod_asr_util.py:12-39), without
+    pandas: keep the FIRST utterance of every distinct label list (order of first appearance), then add
+    n = round(|coverage * N - #distinct|) of the remaining utterances drawn without replacement. The draw reproduces
+    `DataFrame.sample(n, random_state=42)` exactly — pandas takes `RandomState(42).choice(len, n, replace=False)`, which is
+    the first n entries of `RandomState(42).permutation(len)` — so the selected subset is identical to the reference's
+    (tests/test_epoch_host.py checks it against the live reference). Returns index array into the input lists."""
+    n_total = len(label_lists)
+    seen, first = set(), []
+    for i, l in enumerate(label_lists):
+        key = tuple(l)
+        if key not in seen:
+            seen.add(key)
+            first.append(i)
+    first_set = set(first)
+    rest = np.asarray([i for i in range(n_total) if i not in first_set], dtype=np.int64)
+    n_rem = int(np.round(abs(float(coverage) * n_total - len(first))))
+    if n_rem > len(rest):
+        raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+    pick = np.random.RandomState(seed).permutation(len(rest))[:n_rem]
+    return np.concatenate([np.asarray(first, dtype=np.int64), rest[pick]])
+
+
+def read_wcn_data(path, coverage=None):
+    """`read_wcn_data` (utils/dataset/tod_asr_util.py:43-71): (asr word lists, transcript word lists, label lists), with
+    the `--coverage` stratified subset when coverage is given."""
+    asr, trans, labels = read_wcn_lines(path)
+    if coverage:
+        idx = stratified_sample(asr, trans, labels, coverage)
+        asr, trans, labels = [asr[i] for i in idx], [trans[i] for i in idx], [labels[i] for i in idx]
+    return asr, trans, labels
+
+
 def pretokenize(asr_seqs, trans_seqs, label_lists, tokenizer, opt, label2idx, out_dir, chunk=512):
     """Tokenise once with the drop-in `prepare_inputs_for_roberta` and write the flat arrays. Returns out_dir."""
     from .inputs import prepare_inputs_for_roberta
@@ -90,33 +123,52 @@ class PretokenizedDataset:
     def __len__(self):
         return self.n
 
-    def _stream(self, ids, off, seg_start, idx, pinned):
-        lens = (off[idx + 1] - off[idx]).astype(np.int64)
-        S = int(lens.max())
-        out = torch.full((len(idx), S), self.pad, dtype=torch.int64)
-        seg = torch.zeros((len(idx), S), dtype=torch.int64) if self.has_seg else None
-        o, sg = out.numpy(), (seg.numpy() if seg is not None else None)
-        for r, (i, n) in enumerate(zip(idx, lens)):
-            o[r, :n] = ids[off[i]:off[i] + n]
-            if sg is not None:
-                sg[r, seg_start[i]:n] = 1
-        if pinned:
-            out = out.pin_memory()
-            seg = seg.pin_memory() if seg is not None else None
-        return out, seg, [int(x) for x in lens]
+    @staticmethod
+    def _alloc(shape, dtype, pinned, slot, key):
+        """Host tensor for one batch field. With a `slot` dict (Prefetcher ring) the pinned allocation is made once per
+        slot and capacity and then re-used: cudaHostAlloc per batch costs more than assembling the batch."""
+        n = int(np.prod(shape))
+        if slot is None:
+            return torch.empty(shape, dtype=dtype, pin_memory=pinned)
+        buf = slot.get(key)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 2 * (buf.numel() if buf is not None else 0)), dtype=dtype, pin_memory=pinned)
+            slot[key] = buf
+        return buf[:n].view(shape)
 
-    def batch(self, indices, pinned=True):
+    def _stream(self, ids, off, seg_start, idx, pinned, slot, name):
+        """Right-padded [B, S] ids / segment ids of the rows `idx`: one vectorised gather / scatter (no per-row loop)."""
+        lens = (off[idx + 1] - off[idx]).astype(np.int64)
+        B, S, tot = len(idx), int(lens.max()), int(lens.sum())
+        starts = np.cumsum(lens) - lens
+        row = np.repeat(np.arange(B), lens)
+        col = np.arange(tot) - np.repeat(starts, lens)
+        src = np.repeat(off[idx], lens) + col
+        out = self._alloc((B, S), torch.int64, pinned, slot, name + "_ids")
+        o = out.numpy()
+        o.fill(self.pad)
+        o[row, col] = ids[src]
+        seg = None
+        if self.has_seg:
+            seg = self._alloc((B, S), torch.int64, pinned, slot, name + "_seg")
+            sg = seg.numpy()
+            sg.fill(0)
+            sg[row, col] = col >= np.repeat(np.asarray(seg_start[idx], dtype=np.int64), lens)
+        return out, seg, lens.tolist()
+
+    def batch(self, indices, pinned=True, slot=None):
         """dict(ids, seg, lens, trans_ids, trans_seg, trans_lens, labels): host tensors in the reference's padded layout
         (utils/bert_xlnet_inputs.py:91-102) — bit-identical to tokenising these utterances again."""
         idx = np.asarray(indices, dtype=np.int64)
-        ids, seg, lens = self._stream(self.asr_ids, self.asr_off, self.asr_seg, idx, pinned)
-        tids, tseg, tlens = self._stream(self.trans_ids, self.trans_off, self.trans_seg, idx, pinned)
-        labels = torch.zeros((len(idx), self.n_labels), dtype=torch.float32)
+        ids, seg, lens = self._stream(self.asr_ids, self.asr_off, self.asr_seg, idx, pinned, slot, "asr")
+        tids, tseg, tlens = self._stream(self.trans_ids, self.trans_off, self.trans_seg, idx, pinned, slot, "trans")
+        labels = self._alloc((len(idx), self.n_labels), torch.float32, pinned, slot, "labels")
         ln = labels.numpy()
-        for r, i in enumerate(idx):
-            ln[r, self.label_idx[self.label_off[i]:self.label_off[i + 1]]] = 1.0
-        if pinned:
-            labels = labels.pin_memory()
+        ln.fill(0.0)
+        nl = (self.label_off[idx + 1] - self.label_off[idx]).astype(np.int64)
+        if int(nl.sum()):
+            src = np.repeat(self.label_off[idx], nl) + (np.arange(int(nl.sum())) - np.repeat(np.cumsum(nl) - nl, nl))
+            ln[np.repeat(np.arange(len(idx)), nl), self.label_idx[src]] = 1.0
         return dict(ids=ids, seg=seg, lens=lens, trans_ids=tids, trans_seg=tseg, trans_lens=tlens, labels=labels, index=idx)
 
 
@@ -156,9 +208,12 @@ class Prefetcher:
         return len(self.batches)
 
     def _producer(self, q):
+        # ring of pinned staging slots: a slot is re-used only after depth + 3 further batches — the queue holds at most
+        # `depth`, the consumer at most 2 pending copies + the batch in use, and each copy is consumed in stream order
+        ring = [dict() for _ in range(self.depth + 4)]
         try:
-            for idx in self.batches:
-                q.put(self.ds.batch(idx, pinned=self.cuda))
+            for k, idx in enumerate(self.batches):
+                q.put(self.ds.batch(idx, pinned=self.cuda, slot=ring[k % len(ring)]))
         except BaseException as e:          # surfaced in the consumer
             q.put(e)
         q.put(None)

@@ -143,29 +143,53 @@ def _inputs(batch, opt, prepare, pinned_labels=False):
 
 def train_epoch(model, data, opt, memory, trainer=None):
     """Reference train_epoch (n_best_asr_bert.py:232-294): same arguments and return value `(mean_loss, (p, r, f), acc)`.
-    `data` yields the reference's collate_fn tuples. Uses the fused step (`trainer.step`, one optimizer step per batch:
-    the reference's n_accum_steps gradient accumulation is subsumed by data parallelism); metrics and
-    losses accumulate on the device."""
+    `data` yields the reference's collate_fn tuples. Every `opt.n_accum_steps`-th batch takes an optimizer step (:266;
+    the reference sets 4 for 12-layer models, builds its loaders with batchSize / 4 and derives t_total from the full
+    batchSize, :522-556), the batches in between only accumulate gradients; a trailing incomplete group is dropped by
+    the zero_grad at the next epoch start exactly as in the reference (:236). `opt.optim_choice` selects what happens at
+    a step (:268-277): bertadam -> step; adam -> global clip at opt.max_norm + step; adamw -> clip + step +
+    opt.scheduler.step(). Metrics and losses accumulate on the device."""
     from .inputs import prepare_inputs_for_roberta
     from .trainer import DataParallelTrainer
     model.train()
     if trainer is None:
-        trainer = DataParallelTrainer(model, opt.optimizer, add_l2_loss=bool(getattr(opt, "add_l2_loss", False)))
+        trainer = getattr(opt, "_nbest_trainer", None)
+        if trainer is None or trainer.model is not model or trainer.optimizer is not opt.optimizer:
+            trainer = DataParallelTrainer(model, opt.optimizer, add_l2_loss=bool(getattr(opt, "add_l2_loss", False)))
+            opt._nbest_trainer = trainer
     opt.optimizer.zero_grad()
+    n_accum = max(1, int(getattr(opt, "n_accum_steps", 1)))
+    choice = str(getattr(opt, "optim_choice", "bertadam")).lower()
+    clip = float(getattr(opt, "max_norm", 0.0)) if choice != "bertadam" else None
+    sched = getattr(opt, "scheduler", None) if choice == "adamw" else None
     metrics = EpochMetrics(model.device)
-    for batch in data:
+    for step, batch in enumerate(data):
         labels, _, _, ids, seg, lens, tids, tseg, tlens = _inputs(batch, opt, prepare_inputs_for_roberta)
         labels = labels.to(model.device, non_blocking=True)
-        losses = trainer.step(ids, labels, tids, seg, tseg, lens, tlens)
+        if (step + 1) % n_accum == 0:
+            losses = trainer.step(ids, labels, tids, seg, tseg, lens, tlens, clip_norm=clip, scheduler=sched)
+        else:
+            losses = trainer.accumulate(ids, labels, tids, seg, tseg, lens, tlens)
         metrics.update(trainer.last_head.decode, labels, losses)
     return metrics.result()
 
 
+class EpochInfo:
+    """What the reference's EpochInfoCollector carries out of eval_epoch (utils/dataset/tod_asr_util.py:225-242): the
+    per-utterance inputs / predictions / golds / match flags and the epoch's summary numbers."""
+
+    def __init__(self, raw_inputs, whole_pred_classes, true_golds, matches, mean_loss, precision, recall, f1, acc):
+        self.raw_inputs, self.whole_pred_classes, self.true_golds, self.matches = raw_inputs, whole_pred_classes, true_golds, matches
+        self.mean_loss, self.precision, self.recall, self.f1, self.acc = mean_loss, precision, recall, f1, acc
+
+
 def eval_epoch(model, data, opt, memory, fp=None, efp=None):
     """Reference eval_epoch (n_best_asr_bert.py:297-388): forward + loss (no MSE term, :331) + decode + F1 / accuracy,
-    eval mode. Returns `(mean_loss, (p, r, f), acc, cases)`; `cases` (list of (raw, pred_labels, gold_labels)) and the
-    `fp` / `efp` dump lines (:352-357) are only produced when a file object or opt.testing asks for them — that path
-    copies the bitmap to the host once per batch, everything else stays on the device."""
+    eval mode. Returns what the reference returns: `(mean_loss, (p, r, f), acc, eic)`, or
+    `(mean_loss, (p, r, f), acc, all_cases, eic)` when opt.testing (:385-388); `eic` is an EpochInfo (the reference's
+    EpochInfoCollector fields). The per-utterance strings (`all_cases`, eic lists, the `fp` / `efp` dump lines :352-357)
+    are only materialised when a file object or opt.testing asks for them — that path copies the bitmap to the host once
+    per batch; otherwise eic's lists stay empty and everything stays on the device."""
     from .inputs import prepare_inputs_for_roberta
     model.eval()
     want_cases = fp is not None or efp is not None or bool(getattr(opt, "testing", False))
@@ -199,7 +223,11 @@ def eval_epoch(model, data, opt, memory, fp=None, efp=None):
                         efp.write(line)
                     cases.append((raw, pred, gold))
     mean_loss, prf, acc = metrics.result()
-    return mean_loss, prf, acc, cases
+    eic = EpochInfo([" ".join(c[0]) for c in cases], [c[1] for c in cases], [c[2] for c in cases],
+                    [set(c[1]) == set(c[2]) for c in cases], mean_loss, prf[0], prf[1], prf[2], acc)
+    if bool(getattr(opt, "testing", False)):
+        return mean_loss, prf, acc, cases, eic
+    return mean_loss, prf, acc, eic
 
 
 def scores_to_reference_tuple(head, hier):

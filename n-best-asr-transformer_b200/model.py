@@ -29,7 +29,7 @@ H = 768  # reference models/model.py:30 hard-codes fea_dim = 768
 
 @dataclass
 class EncoderSpec:
-    kind: str = "bert"            # "bert" | "xlm-roberta"
+    kind: str = "bert"            # "bert" | "roberta" | "xlm-roberta"  (reference MODEL_CLASSES, n_best_asr_bert.py:33-37)
     vocab_size: int = 30522
     hidden: int = 768
     layers: int = 12
@@ -53,9 +53,22 @@ class EncoderSpec:
         return EncoderSpec(**d)
 
     @staticmethod
+    def roberta_base(**kw):
+        d = dict(kind="roberta", vocab_size=50265, max_position=514, type_vocab=1, ln_eps=1e-5, pad_token_id=1)
+        d.update(kw)
+        return EncoderSpec(**d)
+
+    @property
+    def roberta_style(self):
+        """RoBERTa-family embeddings: position ids = padding_idx + 1 + running count of non-pad tokens, <s> = 0 is
+        masked as a key by the reference's `input_ids > 0` while <pad> = 1 stays attendable."""
+        return self.kind != "bert"
+
+    @staticmethod
     def from_hf(encoder):
         c = encoder.config
-        kind = "xlm-roberta" if "roberta" in getattr(c, "model_type", "bert") else "bert"
+        mt = getattr(c, "model_type", "bert")
+        kind = "xlm-roberta" if mt == "xlm-roberta" else ("roberta" if "roberta" in mt else "bert")
         return EncoderSpec(kind=kind, vocab_size=c.vocab_size, hidden=c.hidden_size, layers=c.num_hidden_layers,
                            heads=c.num_attention_heads, intermediate=c.intermediate_size,
                            max_position=c.max_position_embeddings, type_vocab=c.type_vocab_size, ln_eps=c.layer_norm_eps,
@@ -90,6 +103,10 @@ def _layer_names(l):
                 iw=p + "intermediate.dense.weight", ib=p + "intermediate.dense.bias",
                 ow=p + "output.dense.weight", ob=p + "output.dense.bias",
                 g2=p + "output.LayerNorm.weight", b2=p + "output.LayerNorm.bias")
+
+
+def _describe(t):
+    return "%s %s %s" % (t.device, t.dtype, tuple(t.shape)) if torch.is_tensor(t) else type(t).__name__
 
 
 class _Saved:
@@ -131,6 +148,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
         self.hier = ops.DeviceHierarchy(top2bottom, none_bottoms, device=device)
         self.top2bottom_dict = self.hier.top2bottom
         self._step_seed = int(seed)
+        self._seed_salt = 0      # data-parallel rank salt (trainer): ranks draw independent dropout masks
         # The head (and the MSE term) only ever read the [CLS] row of the last hidden state (reference models/model.py:
         # 46-47,58), so the last layer's attention output, out-projection, FFN and LayerNorms are computed for that row
         # only: ~1/12 less encoder work, identical results (with hidden dropout the compact rows draw a different, equally
@@ -201,7 +219,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
                     v.copy_(torch.randn(v.shape, device=dev, generator=g) * 0.02)
             if encoder_state is None:
                 f.view(f.params, self._index[e + "word_embeddings.weight"])[s.pad_token_id].zero_()
-                if s.kind == "xlm-roberta":
+                if s.roberta_style:
                     f.view(f.params, self._index[e + "position_embeddings.weight"])[1].zero_()
         # ---- nn.Parameters are views of the flat master buffer, .grad views of the flat gradient buffer
         plist = []
@@ -257,9 +275,12 @@ class TOD_ASR_Transformer_STC(nn.Module):
             raise RuntimeError("TOD_ASR_Transformer_STC lives in flat fp32 buffers on %s and cannot be moved or cast" % self.device)
         return self
 
+    # non-parameter buffers that checkpoints written under older transformers versions carry (persistent there)
+    _IGNORED_BUFFERS = ("embeddings.position_ids", "embeddings.token_type_ids")
+
     def load_state_dict(self, state_dict, strict=True, assign=False):
         missing = [n for n in self._names if n not in state_dict]
-        unexpected = [k for k in state_dict if k not in self._index]
+        unexpected = [k for k in state_dict if k not in self._index and not k.endswith(self._IGNORED_BUFFERS)]
         if strict and (missing or unexpected):
             raise RuntimeError("load_state_dict: missing %s unexpected %s" % (missing, unexpected))
         with torch.no_grad():
@@ -293,11 +314,18 @@ class TOD_ASR_Transformer_STC(nn.Module):
         self.flat.grads.zero_()
 
     # ------------------------------------------------------------------------------------------------ packing
-    def _pack_streams(self, input_ids, seg_ids, trans_input_ids, trans_seg_ids, lens=None, trans_lens=None):
+    def _pack_streams(self, input_ids, seg_ids, trans_input_ids, trans_seg_ids, lens=None, trans_lens=None,
+                      drop_token_types=None):
         """Both streams -> ONE packed batch: ASR sequences first (gradient-carrying prefix), then transcripts."""
-        kind = self.spec.kind
-        if kind == "xlm-roberta":
+        kind = "xlm-roberta" if self.spec.roberta_style else "bert"      # packing mode (position ids / key mask)
+        if drop_token_types is None:
+            drop_token_types = self.spec.kind == "xlm-roberta"
+        if drop_token_types:
             seg_ids = trans_seg_ids = None                      # reference models/model.py:42-43: no token types
+        elif self.spec.type_vocab < 2:
+            for t in (seg_ids, trans_seg_ids):                  # HF would raise IndexError in the token-type embedding
+                if t is not None and int(t.max()) >= self.spec.type_vocab:
+                    raise IndexError("token type id %d out of range for type_vocab_size %d" % (int(t.max()), self.spec.type_vocab))
         pa = ops.pack_batch(input_ids, seg_ids, kind, lens)
         if trans_input_ids is None:
             pa.B_asr, pa.T_asr, pa.max_len_asr = pa.B, pa.T, pa.max_len
@@ -315,7 +343,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
         return pk
 
     def _seed(self, layer, site):
-        return (self._step_seed * 1000003 + layer * 16 + site) & 0xFFFFFFFF
+        return ((self._step_seed * 1000003 + layer * 16 + site) ^ self._seed_salt) & 0xFFFFFFFF
 
     # ------------------------------------------------------------------------------------------------ encoder fwd
     def _encode(self, pk, save):
@@ -334,7 +362,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
         sv.mean0, sv.rstd0 = f32(T), f32(T)
         ops.embed_ln_fwd(pk, em["p_word"], em["p_pos"], em["p_type"], em["p_gamma"], em["p_beta"], s.ln_eps, x, sv.mean0,
                          sv.rstd0, p_h, self._seed(0, 15))
-        kv = pk.key_valid if s.kind == "xlm-roberta" else None     # BERT: every in-sequence key is valid (ids > 0)
+        kv = pk.key_valid if s.roberta_style else None             # BERT: every in-sequence key is valid (ids > 0)
         qkv = ctx = pre1 = x1 = u = gact = pre2 = None
         cls_last = self.cls_only_last_layer and s.layers >= 1
         sv.cls_compact = cls_last
@@ -405,7 +433,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
         pk, p_h, p_a = sv.pk, sv.p_h, sv.p_a
         T = pk.T
         bf = lambda *shape: torch.empty(shape, device=dev, dtype=torch.bfloat16)
-        kv = pk.key_valid if s.kind == "xlm-roberta" else None
+        kv = pk.key_valid if s.roberta_style else None
         cu = pk.cu_seqlens[:B_act + 1]
         max_len = pk.max_len_asr if B_act == pk.B_asr and B_act != pk.B else pk.max_len
         dqkv = bf(T_act, 3 * H)
@@ -459,7 +487,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
         em = self._emb
         ops.embed_ln_bwd(pk, em["p_word"], em["p_pos"], em["p_type"], em["p_gamma"], sv.mean0, sv.rstd0, dx, em["g_word"],
                          em["g_pos"], em["g_type"], em["g_gamma"], em["g_beta"], p_h, self._seed(0, 15),
-                         word_pad_row=s.pad_token_id, pos_pad_row=1 if s.kind == "xlm-roberta" else -1, T=T_act)
+                         word_pad_row=s.pad_token_id, pos_pad_row=1 if s.roberta_style else -1, T=T_act)
         self._notify("emb")
 
     def _notify(self, bucket):
@@ -529,7 +557,11 @@ class TOD_ASR_Transformer_STC(nn.Module):
             raise NotImplementedError("return_attns=True is dead code in the reference (models/model.py:70-71 uses an undefined name)")
         need_grad = torch.is_grad_enabled()
         self._step_seed += 1
-        pk = self._pack_streams(input_ids, seg_ids, trans_input_ids, trans_seg_ids, input_lens, trans_input_lens)
+        # models/model.py:42-45: token types are dropped iff opt.pre_trained_model == "xlm-roberta" (the option string, not
+        # the encoder class); a plain opt without the attribute falls back to the encoder kind
+        ptm = getattr(opt, "pre_trained_model", None)
+        drop_tt = (ptm == "xlm-roberta") if ptm else None
+        pk = self._pack_streams(input_ids, seg_ids, trans_input_ids, trans_seg_ids, input_lens, trans_input_lens, drop_tt)
         sv = self._encode(pk, save=need_grad)
         on_trans = classifier_input_type == "transcript" and trans_input_ids is not None
         B = pk.B_asr
@@ -563,6 +595,11 @@ class TOD_ASR_Transformer_STC(nn.Module):
         Returns (losses, head) where losses is a device fp32 tensor [mse, bce_final, bce_top, ce] (no host sync) and head
         carries top/bottom/final scores and the decode bitmap. total = losses.sum(); loss_record = total / B.
         mse_scale lets a data-parallel trainer scale the mean-reduced MSE term by 1/world_size."""
+        nb = self.hier.n_bottom
+        if not (torch.is_tensor(labels) and labels.is_cuda and labels.dtype == torch.float32 and labels.dim() == 2
+                and labels.shape == (input_ids.shape[0], nb) and labels.is_contiguous()):
+            raise ValueError("labels must be a contiguous CUDA float32 [B=%d, %d] multi-hot tensor (collate_fn, "
+                             "tod_asr_util.py:118-130), got %s" % (input_ids.shape[0], nb, _describe(labels)))
         self._step_seed += 1
         pk = self._pack_streams(input_ids, seg_ids, trans_input_ids, trans_seg_ids, input_lens, trans_input_lens)
         sv = self._encode(pk, save=backward)

@@ -55,6 +55,9 @@ def _ctx(t):
     return _lib.context(t.device.index if t.device.index is not None else torch.cuda.current_device())
 
 
+import os as _os
+_CHECK_LENS = _os.environ.get("NBEST_CHECK_LENS", "0") not in ("", "0")
+
 _STREAM = None   # cached cudaStream_t of the stream the current step launches on (torch.cuda.current_stream() costs ~10 us)
 
 
@@ -161,7 +164,7 @@ def _seed(s):
 class Packed:
     """Packed variable-length batch (device tensors). T is a host int (one D2H read of cu_seqlens[-1] unless given)."""
     __slots__ = ("B", "S", "T", "max_len", "lens", "cu_seqlens", "tokens", "seg", "pos", "seq_of", "key_valid",
-                 "B_asr", "T_asr", "max_len_asr")
+                 "B_asr", "T_asr", "max_len_asr", "sum_l2", "sum_l2_asr", "plan", "plan_asr")
 
 
 def pack_batch(ids, seg_ids=None, kind="bert", lens_host=None):
@@ -175,6 +178,8 @@ def pack_batch(ids, seg_ids=None, kind="bert", lens_host=None):
     dev = ids.device
     pk = Packed()
     pk.B, pk.S = B, S
+    pk.sum_l2 = pk.sum_l2_asr = 0.0
+    pk.plan = pk.plan_asr = None
     pk.lens = torch.empty(B, dtype=torch.int32, device=dev)
     pk.cu_seqlens = torch.empty(B + 1, dtype=torch.int32, device=dev)
     cap = B * S
@@ -188,14 +193,35 @@ def pack_batch(ids, seg_ids=None, kind="bert", lens_host=None):
         ctx.check(_lib.lib().nbest_pack_batch(ctx.handle, _p(ids), _p(seg_ids), B, S, 1 if kind == "xlm-roberta" else 0,
                                               _p(pk.lens), _p(pk.cu_seqlens), _p(pk.tokens), _p(pk.seg), _p(pk.pos),
                                               _p(pk.seq_of), _p(pk.key_valid), _stream()))
+    if seg_ids is not None and (seg_ids.dtype != torch.int64 or seg_ids.shape != ids.shape or not seg_ids.is_cuda):
+        raise ValueError("seg_ids must be an int64 CUDA tensor shaped like ids")
     if lens_host is not None and kind != "xlm-roberta":
+        # the kernel derives the true lengths from the ids; the host list only saves the D2H read of T / max_len, so it
+        # must describe THIS batch (input_lens of prepare_inputs_for_roberta): cheap structural checks here, the
+        # device-side truth with NBEST_CHECK_LENS=1
+        if len(lens_host) != B or min(lens_host) < 0 or max(lens_host) > S:
+            raise ValueError("input_lens does not describe ids [%d, %d]: %d entries, max %s" % (B, S, len(lens_host), max(lens_host)))
         pk.T = int(sum(lens_host))
         pk.max_len = int(max(lens_host))
+        pk.sum_l2 = float(sum(int(x) * int(x) for x in lens_host)) if _PROF is not None else 0.0
+        if _CHECK_LENS and pk.lens.cpu().tolist() != [int(x) for x in lens_host]:
+            raise ValueError("input_lens disagrees with the lengths derived from ids")
     else:
         lens_cpu = pk.lens.cpu()
         pk.T = int(lens_cpu.sum())
         pk.max_len = int(lens_cpu.max())
+        pk.sum_l2 = float((lens_cpu.double() ** 2).sum())
     return pk
+
+
+def pack_hyp_ids(pk, sep_id, B=None):
+    """uint8 [T] hypothesis index of every packed token (see nbest_pack_hyp_ids): 0 = [CLS] + system turn + first [SEP]."""
+    B = pk.B if B is None else B
+    out = torch.empty(max(pk.T, 1), dtype=torch.uint8, device=pk.tokens.device)
+    ctx = _ctx(pk.tokens)
+    with _Timed('pack_hyp_ids', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_pack_hyp_ids(ctx.handle, _p(pk.tokens), _p(pk.cu_seqlens), B, int(sep_id), _p(out), _stream()))
+    return out[:pk.T]
 
 
 # ---------------------------------------------------------------------------------------------------------- embed / LN
@@ -365,9 +391,11 @@ def cls_scatter(dcls, cu_seqlens, B, T, dx):
 
 # ---------------------------------------------------------------------------------------------------------- BertAdam
 def bertadam_step(p, g, m, v, p_bf16, tensors_dev, n_tensors, chunks_dev, n_chunks, norms_ws, sched, b1=0.9, b2=0.999,
-                  eps=1e-6, max_grad_norm=1.0):
+                  eps=1e-6, max_grad_norm=1.0, mode=_lib.ADAM_BERT, global_clip=False, step=0):
+    """mode ADAM_BERT: nbest_bertadam_step semantics; ADAM_HF_ADAMW / ADAM_TORCH: see nbest_adam_step."""
     ctx = _ctx(p)
     with _Timed('bertadam_step', 0.0, 0.0):
-        ctx.check(_lib.lib().nbest_bertadam_step(ctx.handle, _p(p), _p(g), _p(m), _p(v), _p(p_bf16), _p(tensors_dev), n_tensors,
-                                                 _p(chunks_dev), n_chunks, _p(norms_ws), float(sched), float(b1), float(b2),
-                                                 float(eps), float(max_grad_norm), _stream()))
+        ctx.check(_lib.lib().nbest_adam_step(ctx.handle, int(mode), _p(p), _p(g), _p(m), _p(v), _p(p_bf16), _p(tensors_dev),
+                                             n_tensors, _p(chunks_dev), n_chunks, _p(norms_ws), float(sched), float(b1),
+                                             float(b2), float(eps), float(max_grad_norm), int(bool(global_clip)), int(step),
+                                             _stream()))

@@ -136,8 +136,13 @@ class DataParallelTrainer:
         if overlap_optimizer is None:
             env = os.environ.get("NBEST_OVERLAP_ADAM")
             overlap_optimizer = (self.world > 1) if env is None else env != "0"
-        self.overlap_optimizer = bool(overlap_optimizer) and hasattr(optimizer, "set_buckets") and \
+        # (AdamW / Adam clip the GLOBAL gradient norm, which needs every gradient before the first update: no buckets)
+        self.overlap_optimizer = bool(overlap_optimizer) and getattr(optimizer, "supports_buckets", False) and \
             getattr(optimizer, "flat", None) is model.flat
+        # independent dropout masks per rank (the counter-based hash is keyed on seed / layer / site / element only);
+        # the base seed in the checkpoint stays rank-free
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        model._seed_salt = (rank * 0x9E3779B1) & 0xFFFFFFFF
         self._bucket_names = {n for n, _, _ in segments}
         if self.overlap_optimizer:
             optimizer.set_buckets(segments)
@@ -168,7 +173,23 @@ class DataParallelTrainer:
             self.optimizer.step_bucket(name)
 
     @ops.with_bound_stream
-    def step(self, ids, labels, trans_ids=None, seg=None, trans_seg=None, lens=None, trans_lens=None):
+    def accumulate(self, ids, labels, trans_ids=None, seg=None, trans_seg=None, lens=None, trans_lens=None):
+        """Forward + loss + backward of one micro-batch INTO the flat gradient buffer, without exchange or update: the
+        first n_accum_steps - 1 micro-batches of the reference's gradient accumulation (n_best_asr_bert.py:264-266; the
+        wgrad kernels accumulate with fp32 red.add, so nothing else is needed). The micro-batch that completes the
+        group goes through step(), whose bucketed all-reduce then carries the accumulated sums."""
+        m = self.model
+        m._grad_ready_hook = None
+        losses, head = m.forward_loss_backward(ids, labels, trans_ids, seg, trans_seg, add_l2_loss=self.add_l2_loss,
+                                               mse_scale=1.0 / self.world, input_lens=lens, trans_input_lens=trans_lens)
+        self.last_head = head
+        return losses
+
+    @ops.with_bound_stream
+    def step(self, ids, labels, trans_ids=None, seg=None, trans_seg=None, lens=None, trans_lens=None, clip_norm=None,
+             scheduler=None):
+        """clip_norm: global gradient-norm clip folded into an AdamW / Adam update (n_best_asr_bert.py:268-271);
+        scheduler: stepped after the update (adamw branch, :276-277)."""
         m = self.model
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())     # zeroed grads / previous step are visible
@@ -192,7 +213,12 @@ class DataParallelTrainer:
             torch.cuda.current_stream().wait_stream(self.opt_stream)
             self.optimizer.end_bucketed_step()
         else:
+            if clip_norm is not None and clip_norm > 0:
+                from .optim import clip_grad_norm_
+                clip_grad_norm_(m._plist, clip_norm, optimizer=self.optimizer)
             self.optimizer.step()
+        if scheduler is not None:
+            scheduler.step()
         self.optimizer.zero_grad()
         self.last_head = head
         return losses

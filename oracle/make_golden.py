@@ -309,7 +309,42 @@ def epoch_case(nb, m):
     print("epoch fixture: B", B, "counts", counts, "filtered", counts_f, "unk golds", int(labels[:, 1].sum()))
 
 
+def export_coverage():
+    """`--coverage` stratified sampler (utils/dataset/tod_asr_util.py:12-39, pandas) run by the live reference on the
+    shipped valid file -> tests/golden/coverage_valid.npz: the integer-coded label list of every utterance (all the
+    sampler looks at) and, per coverage value, which utterances the reference kept, in its order."""
+    import contextlib
+    import io
+    import_reference()
+    import utils.dataset.tod_asr_util as tod
+    fn = os.path.join(REF, "dstc2_data/processed_data/raw/valid")
+    asr, trans, labels = tod.read_wcn_data(fn)
+    codes, code_of = [], {}
+    for l in labels:
+        codes.append(code_of.setdefault(tuple(l), len(code_of)))
+    pos = {}
+    for i, (a, t) in enumerate(zip(asr, trans)):
+        pos.setdefault((tuple(a), tuple(t), tuple(labels[i])), []).append(i)
+    out = dict(label_code=np.asarray(codes, dtype=np.int32))
+    for cov in (0.1, 0.25, 0.5):
+        with contextlib.redirect_stdout(io.StringIO()):
+            a2, t2, l2 = tod.read_wcn_data(fn, cov)
+        used, idx = {}, []
+        for a, t, l in zip(a2, t2, l2):            # map the sampled rows back to line numbers (duplicates in file order)
+            key = (tuple(a), tuple(t), tuple(l))
+            k = used.get(key, 0)
+            idx.append(pos[key][k] if k < len(pos[key]) else pos[key][-1])
+            used[key] = k + 1
+        out["count_%g" % cov] = np.asarray([len(a2)], dtype=np.int64)
+        out["labels_%g" % cov] = np.asarray([code_of[tuple(l)] for l in l2], dtype=np.int32)
+        out["index_%g" % cov] = np.asarray(idx, dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLD, "coverage_valid.npz"), **out)
+    print("coverage fixture:", {k: v.shape for k, v in out.items()})
+
+
 def main():
+    if "--coverage-only" in sys.argv:
+        return export_coverage()
     if "--epoch-only" in sys.argv:
         refmods = import_reference()
         m = torch.load(os.path.join(REF, "dstc2_data/processed_data/raw/memory.pt"))

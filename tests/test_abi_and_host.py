@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), "libnbest_sm100.so does not export %s" % name
     assert sorted(_lib.exported_symbols()) == declared, "ctypes signature table and header disagree"
     lib.nbest_abi_version.restype = ctypes.c_int
-    assert lib.nbest_abi_version() == 1
+    assert lib.nbest_abi_version() == 2
 
 
 def test_header_cites_reference_for_every_entry_point():
@@ -221,6 +221,10 @@ def test_bench_reference_arm_prints_one_contract_line():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "utterances/s" and d["value"] > 0 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference" = the unmodified reference staged under oracle/_ref (or /root/reference here); "port" only without it
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_loader
+    if ref_loader.available():
+        assert d["cpu_baseline"]["kind"] == "reference" and set(d["cpu_baseline"]["split"]) == {"fwd_ms", "bwd_ms", "optimizer_ms"}
     assert d["e2e"] == dict(value=d["value"], unit=d["unit"], h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     assert "workload" in d["config"] and "model" not in d["config"]

@@ -137,3 +137,24 @@ def test_prefetcher_yields_the_dataset_batches_in_order_on_cpu(tmp_path):
         ref = ds.batch(idx, pinned=False)
         assert torch.equal(b["ids"], ref["ids"]) and torch.equal(b["seg"], ref["seg"]) and b["lens"] == ref["lens"]
         assert torch.equal(b["labels"], ref["labels"])
+
+
+def test_coverage_sampler_equals_the_reference_pandas_sampler():
+    """`--coverage` (utils/dataset/tod_asr_util.py:12-39): the numpy restatement keeps exactly the utterances the live
+    reference's pandas sampler kept on the shipped valid file (fixture: oracle/make_golden.py --coverage-only). The
+    sampler only looks at the label lists, so the fixture stores them integer-coded."""
+    from nbest_b200.data import stratified_sample
+    fx = np.load(os.path.join(GOLD, "coverage_valid.npz"))
+    labels = [[str(c)] for c in fx["label_code"]]
+    n = len(labels)
+    for cov in (0.1, 0.25, 0.5):
+        idx = stratified_sample([None] * n, [None] * n, labels, cov)
+        assert len(idx) == int(fx["count_%g" % cov][0])
+        assert np.array_equal(fx["label_code"][idx], fx["labels_%g" % cov])          # same label sequence, same order
+        assert len(set(idx.tolist())) == len(idx)                                      # without replacement
+    # first occurrences come first, in file order
+    first = stratified_sample([None] * n, [None] * n, labels, 0.1)[:len(set(fx["label_code"].tolist()))]
+    assert np.array_equal(first, np.sort(first)) and len(set(fx["label_code"][first].tolist())) == len(first)
+    import pytest
+    with pytest.raises(ValueError):
+        stratified_sample([None] * 4, [None] * 4, [["a"], ["a"], ["b"], ["b"]], 2.0)   # n > population, like pandas

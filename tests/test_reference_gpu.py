@@ -1,0 +1,400 @@
+"""Parity against THE REFERENCE ITSELF on the GPU box: the unmodified modules staged under oracle/_ref/ (oracle/vendor_ref.py)
+run on the same B200 in fp32 next to the drop-ins.
+
+  (a) make_model(opt) ingesting a live HuggingFace encoder (BertModel / RobertaModel / XLMRobertaModel) == the reference
+      module on the same encoder; save_model -> the reference's load_model round trip;
+  (b) the reference's own train_epoch (n_best_asr_bert.py:232-294) hosting the three swapped imports of INTEGRATION.md §2,
+      against the stock run and against the fused epoch mirror (values, not just "loss decreases"), incl. n_accum_steps;
+  (c) the BASELINE configs[1] step (BERT-base, B = 256) against the oracle;
+  (d) XLM-R-base with its full 250,002-row vocabulary against the oracle, padding_idx rows included;
+  (e) --optim_choice adam / adamw trajectories against torch.optim.Adam / the transformers-2.3.0 AdamW restatement.
+Tolerances (BASELINE.json): scores max|d|/max|ref| <= 2e-2, per-tensor gradient cosine >= 0.999, counters +-2 labels.
+"""
+import io
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.dirname(__file__))
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 2e-2
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _cos(a, b):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def _ref():
+    from oracle import ref_loader as R
+    if not R.available():
+        pytest.skip("reference not staged (python oracle/vendor_ref.py)")
+    return R, R.load()
+
+
+def _batch(kind, vocab, B, max_len, seed, n_hyps=5):
+    from nbest_b200.synth import synth_batch
+    from oracle import stc_oracle as O
+    hj = json.load(open(os.path.join(GOLD, "dstc2_hierarchy.json")))
+    hier = O.Hierarchy({int(k): v for k, v in hj["top2bottom"].items()}, hj["none_bottoms"])
+    return synth_batch(kind, vocab, hier, B=B, n_hyps=n_hyps, max_len=max_len, seed=seed), hier, hj
+
+
+# ------------------------------------------------------------------------------------------------ (a)
+@pytest.mark.parametrize("kind", ["bert", "xlm-roberta", "roberta"])
+def test_make_model_from_live_hf_encoder_matches_reference_module(kind, tmp_path):
+    from nbest_b200.model import make_model
+    R, ref = _ref()
+    torch.manual_seed(11)
+    small = dict(num_hidden_layers=3)
+    if kind == "bert":
+        enc = R.hf_encoder("bert", **small)
+    elif kind == "roberta":
+        enc = R.hf_encoder("roberta", vocab_size=6000, **small)
+    else:
+        enc = R.hf_encoder("xlm-roberta", vocab_size=9000, **small)
+    with torch.no_grad():      # default init leaves LayerNorm at (1, 0) and biases at 0: perturb so that they matter
+        for n, p in enc.named_parameters():
+            if "LayerNorm" in n or n.endswith(".bias"):
+                p.add_(0.05 * torch.randn_like(p))
+    mem = R.memory("cuda")
+    opt = R.make_opt(enc, mem, "cuda", pre_trained_model=kind, dropout=0.3)
+    ours = make_model(opt)                                  # ingests opt.pretrained_model's weights
+    theirs = ref.make_model(opt).to("cuda").eval()
+    ours.load_state_dict({k: v for k, v in theirs.state_dict().items() if k.startswith("clf.")}, strict=False)
+    ours.eval()
+    vocab = enc.config.vocab_size
+    batch, hier, hj = _batch("bert" if kind == "bert" else "xlm-roberta", vocab, B=12, max_len=96, seed=3)
+    d = lambda k: batch[k].cuda()
+    seg, tseg = (d("seg"), d("trans_seg")) if kind == "bert" else (None, None)
+    if kind == "xlm-roberta":                               # the reference drops token types for XLM-R whatever is passed
+        seg, tseg = d("seg"), d("trans_seg")
+    with torch.no_grad():
+        a = ours(opt, d("ids"), d("trans_ids"), seg_ids=seg, trans_seg_ids=tseg)
+        b = theirs(opt, d("ids"), d("trans_ids"), seg_ids=seg, trans_seg_ids=tseg)
+    assert _rel(a[0], b[0]) <= TOL and _rel(a[2], b[2]) <= TOL
+    assert _rel(a[3], b[3]) <= TOL and _rel(a[4], b[4]) <= TOL
+    for k in b[1]:
+        assert _rel(a[1][k], b[1][k]) <= TOL, k
+    # transcript-fed classifier (classifier_input_type="transcript", models/model.py:60-63)
+    with torch.no_grad():
+        a2 = ours(opt, d("ids"), d("trans_ids"), seg_ids=seg, trans_seg_ids=tseg, classifier_input_type="transcript")
+        b2 = theirs(opt, d("ids"), d("trans_ids"), seg_ids=seg, trans_seg_ids=tseg, classifier_input_type="transcript")
+    assert _rel(a2[0], b2[0]) <= TOL and _rel(a2[2], b2[2]) <= TOL
+    # state_dict keys and save_model -> reference load_model
+    assert list(ours.state_dict().keys()) == [k for k in theirs.state_dict().keys()] or \
+        set(ours.state_dict().keys()) == set(theirs.state_dict().keys())
+    path = str(tmp_path / "model.pt")
+    ours.save_model(path)
+    enc2 = R.hf_encoder(kind, **(small if kind == "bert" else dict(vocab_size=vocab, **small)))
+    theirs2 = ref.make_model(R.make_opt(enc2, mem, "cuda", pre_trained_model=kind)).to("cuda").eval()
+    theirs2.load_model(path)
+    with torch.no_grad():
+        c = theirs2(opt, d("ids"), d("trans_ids"), seg_ids=seg, trans_seg_ids=tseg)
+    assert _rel(c[0], b[0]) < 1e-5 and _rel(c[2], b[2]) < 1e-5          # same fp32 weights -> same fp32 reference output
+    # and the other direction: a reference checkpoint loads into the drop-in
+    theirs.save_model(path)
+    ours.load_model(path)
+    with torch.no_grad():
+        a3 = ours(opt, d("ids"), d("trans_ids"), seg_ids=seg, trans_seg_ids=tseg)
+    assert _rel(a3[0], b[0]) <= TOL
+
+
+def test_roberta_rejects_token_types_like_the_reference():
+    """roberta-base has ONE token type: the reference passes trans_seg_ids for `roberta` (models/model.py:44-45,55-56)
+    and HF raises an index error on the [0..1] ids; it only runs with --without_system_act (no segment ids)."""
+    from nbest_b200.model import make_model
+    R, ref = _ref()
+    enc = R.hf_encoder("roberta", vocab_size=3000, num_hidden_layers=1)
+    opt = R.make_opt(enc, R.memory("cuda"), "cuda", pre_trained_model="roberta")
+    ours = make_model(opt).eval()
+    batch, _, _ = _batch("xlm-roberta", 3000, B=4, max_len=40, seed=1)
+    with pytest.raises(IndexError):
+        ours(opt, batch["ids"].cuda(), None, seg_ids=batch["seg"].cuda())
+
+
+# ------------------------------------------------------------------------------------------------ (b)
+def _epoch_data(ref, R, mem, n, bs, device):
+    asr, trans, labels = ref.tod.read_wcn_data(R.valid_path())
+    data = (asr[:n], trans[:n], labels[:n])
+    return ref.tod.prepare_wcn_dataloader(data, mem, bs, None, device, shuffle_flag=False)
+
+
+@pytest.mark.parametrize("n_accum", [1, 2])
+def test_reference_train_epoch_stock_vs_swapped_imports_vs_fused_mirror(n_accum):
+    """The reference's train_epoch is run three ways on the same 96 real utterances (6 batches of 16, fake tokenizer,
+    dropout 0, 2-layer BERT, --add_l2_loss on): (1) stock; (2) with make_model / BertAdam / prepare_inputs_for_roberta
+    swapped for the drop-ins — its own loop, cal_total_loss and pred_one_sample drive our forward /
+    backward / optimizer; (3) our epoch.train_epoch mirror with the fused step. Losses, P/R/F and accuracy must agree."""
+    from fake_tokenizer import FakeTok
+    from nbest_b200 import epoch as E
+    from nbest_b200.inputs import prepare_inputs_for_roberta as our_prepare
+    from nbest_b200.model import make_model as our_make_model
+    from nbest_b200.optim import BertAdam as OurBertAdam
+    from nbest_b200.driver import grouped_parameters
+    R, ref = _ref()
+    nb = ref.nb
+    mem = R.memory("cuda")
+    results = {}
+    for mode in ("stock", "swapped", "mirror"):
+        torch.manual_seed(5)
+        enc = R.hf_encoder("bert", num_hidden_layers=2, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+        opt = R.make_opt(enc, mem, "cuda", pre_trained_model="bert", dropout=0.0, add_l2_loss=True, n_accum_steps=n_accum,
+                         tokenizer=FakeTok())
+        torch.manual_seed(6)                                # same head init for the three runs (nn.Linear default init)
+        theirs = ref.make_model(opt).to("cuda")
+        head = {k: v.clone() for k, v in theirs.state_dict().items() if k.startswith("clf.")}
+        if mode == "stock":
+            model = theirs
+            groups = grouped_parameters(model, 1e-3, 2e-4)
+            opt.optimizer = ref.BertAdam(groups, lr=1e-3, warmup=0.1, t_total=30)
+        else:
+            model = our_make_model(opt)
+            model.load_state_dict(head, strict=False)
+            opt.optimizer = OurBertAdam(grouped_parameters(model, 1e-3, 2e-4), lr=1e-3, warmup=0.1, t_total=30)
+        data = _epoch_data(ref, R, mem, 96, 16, torch.device("cuda"))
+        out = []
+        for ep in range(2):
+            if mode == "mirror":
+                out.append(E.train_epoch(model, data, opt, mem))
+            else:
+                saved = nb.prepare_inputs_for_roberta
+                if mode == "swapped":
+                    nb.prepare_inputs_for_roberta = our_prepare
+                try:
+                    sink = io.StringIO()
+                    stdout, sys.stdout = sys.stdout, sink           # cal_total_loss prints the MSE term every step
+                    try:
+                        out.append(nb.train_epoch(model, data, opt, mem))
+                    finally:
+                        sys.stdout = stdout
+                finally:
+                    nb.prepare_inputs_for_roberta = saved
+        results[mode] = out
+    for mode in ("swapped", "mirror"):
+        for ep in range(2):
+            l0, (p0, r0, f0), a0 = results["stock"][ep]
+            l1, (p1, r1, f1), a1 = results[mode][ep]
+            assert abs(l1 - l0) <= 1e-2 * abs(l0), (mode, ep, l0, l1)
+            # 96 utterances, ~130 gold labels: a label flipping at the 0.5 threshold moves P/R/F by < 1 point
+            assert abs(p1 - p0) <= 2.5 and abs(r1 - r0) <= 2.5 and abs(f1 - f0) <= 2.5, (mode, ep, (p0, r0, f0), (p1, r1, f1))
+            assert abs(a1 - a0) <= 100.0 * 2 / 96 + 1e-9, (mode, ep, a0, a1)
+    # the second epoch really trained (the loss moved) and all three agree on by how much
+    assert results["stock"][1][0] < results["stock"][0][0]
+
+
+def test_eval_epoch_return_contract_and_values_vs_reference():
+    from fake_tokenizer import FakeTok
+    from nbest_b200 import epoch as E
+    from nbest_b200.model import make_model as our_make_model
+    R, ref = _ref()
+    mem = R.memory("cuda")
+    torch.manual_seed(9)
+    enc = R.hf_encoder("bert", num_hidden_layers=2)
+    opt = R.make_opt(enc, mem, "cuda", pre_trained_model="bert", dropout=0.3, tokenizer=FakeTok())
+    theirs = ref.make_model(opt).to("cuda")
+    ours = our_make_model(opt)
+    ours.load_state_dict({k: v for k, v in theirs.state_dict().items() if k.startswith("clf.")}, strict=False)
+    data = _epoch_data(ref, R, mem, 64, 16, torch.device("cuda"))
+    fa, ea, fb, eb = io.StringIO(), io.StringIO(), io.StringIO(), io.StringIO()
+    with torch.no_grad():
+        ra = ref.nb.eval_epoch(theirs, data, opt, mem, fa, ea)
+    rb = E.eval_epoch(ours, data, opt, mem, fb, eb)
+    assert len(ra) == len(rb) == 4
+    assert abs(rb[0] - ra[0]) <= 1e-2 * abs(ra[0])
+    la, lb = fa.getvalue().split("\n"), fb.getvalue().split("\n")
+    assert len(la) == len(lb) == 65
+    assert sum(x != y for x, y in zip(la, lb)) <= 2                # identical dump lines up to threshold flips
+    assert abs(rb[2] - ra[2]) <= 100.0 * 2 / 64 + 1e-9
+    eic = rb[3]
+    assert len(eic.raw_inputs) == 64 and len(eic.matches) == 64 and eic.f1 == rb[1][2]
+    opt.testing = True
+    rc = E.eval_epoch(ours, data, opt, mem, None, None)
+    assert len(rc) == 5 and len(rc[3]) == 64
+
+
+# ------------------------------------------------------------------------------------------------ (c)
+def test_baseline_config_b256_step_matches_oracle():
+    """BASELINE configs[1]: BERT-base, 5-best, max_len 128, B = 256 (12.2 k + 5.8 k tokens), transcript stream forward-only
+    (no --add_l2_loss) — one full training step's scores, loss terms and every gradient tensor against the CPU oracle.
+    The oracle walks the batch in 4 slices of 64 utterances (each ~6 GB of fp32 autograd state, ~10 s of host time) and
+    sums loss terms and gradients: every class-loss term is SUM-reduced over the batch (n_best_asr_bert.py:572-573)."""
+    from oracle import stc_oracle as O
+    from nbest_b200.model import EncoderSpec, TOD_ASR_Transformer_STC
+    torch.set_num_threads(os.cpu_count())
+    batch, hier, hj = _batch("bert", 30522, B=256, max_len=128, seed=999)
+    cfg = O.EncoderConfig.bert_base()
+    params = O.init_params(cfg, hier, seed=5, style="perturbed")
+    keys = ("ids", "seg", "trans_ids", "trans_seg", "labels")
+    tot_terms, tot_grads, tops, finals, transs = {}, {}, [], [], []
+    for s0 in range(0, 256, 64):
+        sub = {k: batch[k][s0:s0 + 64] for k in keys}
+        S, St = int((sub["ids"] > 0).sum(1).max()), int((sub["trans_ids"] > 0).sum(1).max())
+        sub["ids"], sub["seg"] = sub["ids"][:, :S].contiguous(), sub["seg"][:, :S].contiguous()
+        sub["trans_ids"], sub["trans_seg"] = sub["trans_ids"][:, :St].contiguous(), sub["trans_seg"][:, :St].contiguous()
+        terms, grads, (top, bottoms, final, asr, trans) = O.train_step(params, cfg, hier, sub, None, dict(add_l2_loss=False))
+        for k, v in terms.items():
+            tot_terms[k] = tot_terms.get(k, 0.0) + v
+        for k, g in grads.items():
+            if g is not None:
+                tot_grads[k] = g if k not in tot_grads else tot_grads[k] + g
+        tops.append(top.detach())
+        finals.append(final.detach())
+        transs.append(trans.detach())
+        del grads, top, bottoms, final, asr, trans
+    spec = EncoderSpec.bert_base(hidden_dropout=0.0, attn_dropout=0.0)
+    model = TOD_ASR_Transformer_STC(spec=spec, top2bottom=hier.top2bottom, dropout=0.0, device="cuda",
+                                    none_bottoms=hj["none_bottoms"])
+    model.load_state_dict(params)
+    model.train()
+    model.zero_grad()
+    d = lambda k: batch[k].cuda()
+    losses, ho = model.forward_loss_backward(d("ids"), d("labels"), d("trans_ids"), d("seg"), d("trans_seg"), add_l2_loss=False,
+                                             input_lens=batch["lens"], trans_input_lens=batch["trans_lens"])
+    assert _rel(ho.top, torch.cat(tops)) <= TOL and _rel(ho.final, torch.cat(finals)) <= TOL
+    err = ho.trans_cls.double().cpu() - torch.cat(transs).double()
+    assert float(err.norm() / torch.cat(transs).double().norm()) <= TOL          # forward-only transcript stream
+    ref_terms = torch.tensor([tot_terms["bce_final"], tot_terms["bce_top"], tot_terms["ce"]])
+    assert float(losses[0]) == 0.0 and _rel(losses[1:], ref_terms) <= 1e-2, (losses, ref_terms)
+    worst = (1.0, None)
+    named = dict(model.named_parameters())
+    for n, g in tot_grads.items():
+        if "attention.self.key.bias" in n:
+            continue
+        c = _cos(named[n].grad, g)
+        worst = min(worst, (c, n))
+        assert c >= 0.999, (n, c)
+        nr = float(g.double().norm())
+        assert abs(float(named[n].grad.double().norm()) - nr) <= 0.05 * nr + 1e-7, n
+    print("B=256 worst gradient cosine vs oracle:", worst)
+
+
+# ------------------------------------------------------------------------------------------------ (d)
+def test_xlmr_base_full_vocab_matches_oracle_including_padding_rows():
+    """BASELINE configs[2] shape: XLM-R-base with the real 250,002 x 768 embedding table (4 layers keep the CPU oracle
+    at seconds; the embedding scatter, the pad-as-real-work rows and the padding_idx zero-gradient rows do not depend on
+    depth), B = 24 ragged rows so that <pad> = 1 tokens are attended and position id 1 is used."""
+    from oracle import stc_oracle as O
+    from nbest_b200.model import EncoderSpec, TOD_ASR_Transformer_STC
+    torch.set_num_threads(os.cpu_count())
+    batch, hier, hj = _batch("xlm-roberta", 250002, B=24, max_len=128, seed=17)
+    cfg = O.EncoderConfig.xlmr_base(layers=4)
+    params = O.init_params(cfg, hier, seed=8, style="perturbed")
+    terms, grads, (top, bottoms, final, asr, trans) = O.train_step(
+        {k: v.clone() for k, v in params.items()}, cfg, hier, batch, None, dict(add_l2_loss=True))
+    spec = EncoderSpec.xlmr_base(layers=4, hidden_dropout=0.0, attn_dropout=0.0)
+    model = TOD_ASR_Transformer_STC(spec=spec, top2bottom=hier.top2bottom, dropout=0.0, device="cuda",
+                                    none_bottoms=hj["none_bottoms"])
+    model.load_state_dict(params)
+    model.train()
+    model.zero_grad()
+    d = lambda k: batch[k].cuda()
+    losses, ho = model.forward_loss_backward(d("ids"), d("labels"), d("trans_ids"), d("seg"), d("trans_seg"), add_l2_loss=True)
+    assert _rel(ho.top, top) <= TOL and _rel(ho.final, final) <= TOL
+    ref_terms = torch.tensor([terms["mse"], terms["bce_final"], terms["bce_top"], terms["ce"]])
+    assert _rel(losses, ref_terms) <= 1e-2
+    named = dict(model.named_parameters())
+    for n, g in grads.items():
+        if g is None or "attention.self.key.bias" in n:
+            continue
+        assert _cos(named[n].grad, g) >= 0.999, (n, _cos(named[n].grad, g))
+    we = named["bert_encoder.embeddings.word_embeddings.weight"].grad
+    pe = named["bert_encoder.embeddings.position_embeddings.weight"].grad
+    assert float(we[1].abs().max()) == 0.0 and float(pe[1].abs().max()) == 0.0        # padding_idx rows
+    assert int((batch["ids"] == 1).sum()) > 0                                         # ... and pads really were present
+    touched = torch.unique(batch["ids"]).numel() + torch.unique(batch["trans_ids"]).numel()
+    assert int((we.abs().sum(1) > 0).sum()) <= touched                                # row-sparse: only seen ids have gradient
+    # the token-type table has one row and XLM-R never receives token types (models/model.py:42-43): gradient = sum over tokens
+    assert _cos(named["bert_encoder.embeddings.token_type_embeddings.weight"].grad,
+                grads["bert_encoder.embeddings.token_type_embeddings.weight"]) >= 0.999
+
+
+# ------------------------------------------------------------------------------------------------ (e)
+def _hf_adamw_230(params, grads, state, lr, wd, b1=0.9, b2=0.999, eps=1e-6):
+    """transformers 2.3.0 optimization.py AdamW.step, correct_bias=False (restated; the class no longer exists in 5.x)."""
+    for k in params:
+        g = grads[k]
+        m, v = state.setdefault(k, (torch.zeros_like(g), torch.zeros_like(g)))
+        m.mul_(b1).add_(g, alpha=1 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        params[k].addcdiv_(m, v.sqrt().add_(eps), value=-lr[k])
+        if wd[k] > 0:
+            params[k].add_(params[k], alpha=-lr[k] * wd[k])
+
+
+@pytest.mark.parametrize("choice", ["adam", "adamw"])
+def test_optim_choice_adam_adamw_with_global_clip(choice):
+    """n_best_asr_bert.py:268-277,553-569: global clip_grad_norm_(params, max_norm) then Adam.step / AdamW.step +
+    scheduler.step — on the fused kernel vs torch.optim.Adam / the AdamW restatement on the same gradients, 5 steps."""
+    from nbest_b200 import optim as NO
+    torch.manual_seed(3)
+    shapes = [(300, 768), (768,), (171,), (64, 3), (1,)]
+    ours = [torch.nn.Parameter(torch.randn(s, device="cuda") * 0.1) for s in shapes]
+    ref_p = [p.detach().clone().requires_grad_(True) for p in ours]
+    lrs = [1e-3, 1e-3, 5e-3, 5e-3, 5e-3]
+    wds = [0.01, 0.0, 0.01, 0.0, 0.0]
+    max_norm, total, warm = 5.0, 20, 2
+    if choice == "adam":
+        o = NO.Adam(ours, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+        r = torch.optim.Adam(ref_p, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+        sched = None
+    else:
+        o = NO.AdamW([dict(params=p, lr=l, weight_decay=w) for p, l, w in zip(ours, lrs, wds)], lr=1e-3, correct_bias=False)
+        sched = NO.get_linear_schedule_with_warmup(o, warm, total)
+        state = {}
+    for step in range(5):
+        gs = [torch.randn(s, device="cuda") * (3.0 if step % 2 == 0 else 0.01) for s in shapes]   # clipped / unclipped steps
+        for p, g in zip(ours, gs):
+            p.grad.copy_(g) if p.grad is not None else setattr(p, "grad", g.clone())
+        NO.clip_grad_norm_(ours, max_norm, optimizer=o)
+        o.step()
+        if sched is not None:
+            sched.step()
+        for p, g in zip(ref_p, gs):
+            p.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_(ref_p, max_norm)
+        if choice == "adam":
+            r.step()
+        else:
+            lam = (step / warm) if step < warm else max(0.0, (total - step) / (total - warm))
+            with torch.no_grad():
+                _hf_adamw_230({i: p for i, p in enumerate(ref_p)}, {i: p.grad for i, p in enumerate(ref_p)}, state,
+                              {i: l * lam for i, l in enumerate(lrs)}, dict(enumerate(wds)))
+        for a, b in zip(ours, ref_p):
+            assert _rel(a, b) <= 3e-6, (choice, step, _rel(a, b))
+
+
+def test_optimizer_state_dict_round_trip():
+    from nbest_b200 import optim as NO
+    torch.manual_seed(1)
+    mk = lambda: [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in [(64, 64), (64,)]]
+    pa, pb = mk(), None
+    oa = NO.BertAdam([dict(params=p, lr=1e-3, weight_decay=0.01) for p in pa], lr=1e-3, warmup=0.1, t_total=10)
+    for _ in range(3):
+        for p in pa:
+            p.grad.copy_(torch.randn_like(p)) if p.grad is not None else setattr(p, "grad", torch.randn_like(p))
+        oa.step()
+    sd = oa.state_dict()
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    ob = NO.BertAdam([dict(params=p, lr=1e-3, weight_decay=0.01) for p in pb], lr=1e-3, warmup=0.1, t_total=10)
+    ob.load_state_dict(sd)
+    g = [torch.randn_like(p) for p in pa]
+    for o, ps in ((oa, pa), (ob, pb)):
+        for p, gg in zip(ps, g):
+            p.grad.copy_(gg) if p.grad is not None else setattr(p, "grad", gg.clone())
+        o.step()
+    for a, b in zip(pa, pb):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        NO.BertAdam([dict(params=pa[0], lr=1e-3, b1=0.9), dict(params=pa[1], lr=1e-3, b1=0.8)], lr=1e-3, warmup=0.1, t_total=10).step()
