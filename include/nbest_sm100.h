@@ -148,6 +148,39 @@ int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* c
                           const float* lse, void* dqkv_bf16, float* delta_ws, float p_drop, uint32_t seed,
                           void* stream);
 
+/* ---- attention on the tcgen05 tensor path for packed SHORT sequences (<= 128 tokens) ----------------------- */
+/* Same math and same dropout index map as nbest_attn_varlen_fwd/bwd (modeling_bert.py:115-140,192-205 under the key
+ * mask of models/model.py:43,45), organised for Blackwell: whole sequences are packed into 128-row tiles of the
+ * packed token axis, one work item = (tile, head) computes S = Q K^T as ONE 128x128x64 tcgen05.mma chain with a
+ * block-diagonal (same-sequence) mask, softmax / dropout out of TMEM, O = P V as a 128x64x128 chain; Q/K/V/dO tiles
+ * arrive by TMA, persistent CTAs. Sequences longer than 128 tokens are NOT touched: run nbest_attn_varlen_fwd2/bwd2
+ * with min_len = 129 for them (counts[2] tells whether there are any).
+ *
+ * nbest_attn_plan: tiles[2*i] = first packed row, tiles[2*i+1] = rows of tile i (capacity B tiles); counts[0] = number
+ * of tiles, counts[1] = number of tiles covering sequences [0, break_at) (no tile straddles break_at: the backward of
+ * the ASR prefix uses count_idx = 1), counts[2] = number of sequences longer than 128; row_bounds[2*t], [2*t+1] =
+ * first / one-past-last packed row of token t's sequence. cu_seqlens / seq_of are nbest_pack_batch outputs. */
+int nbest_attn_plan(nbest_ctx* ctx, const int32_t* cu_seqlens, const int32_t* seq_of, int B, int T, int break_at,
+                    int32_t* tiles, int32_t* counts, int32_t* row_bounds, void* stream);
+/* max_tiles: host-side upper bound of counts[count_idx] (B is always one); sizes the persistent grid. */
+int nbest_attn_tiles_fwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* tiles, const int32_t* counts, int count_idx,
+                         int max_tiles, const int32_t* row_bounds, const uint8_t* key_valid, int heads, int T,
+                         void* out_bf16, float* lse, float p_drop, uint32_t seed, void* stream);
+/* delta[h * delta_pitch + t] = rowsum(dO * O) per head (the out-projection dgrad's NBEST_EPI_DELTA epilogue writes
+ * it). dout is [T_active, heads*64]; gradients are written for the tiles' own rows only. */
+int nbest_attn_tiles_bwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* tiles, const int32_t* counts, int count_idx,
+                         int max_tiles, const int32_t* row_bounds, const uint8_t* key_valid, int heads, int T, int T_active,
+                         const void* dout_bf16, const float* lse, const float* delta, int delta_pitch, void* dqkv_bf16,
+                         float p_drop, uint32_t seed, void* stream);
+/* nbest_attn_varlen_fwd / _bwd restricted to sequences of at least min_len tokens (0 = all). */
+int nbest_attn_varlen_fwd2(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens, const uint8_t* key_valid,
+                           int B, int max_len, int heads, int T, void* out_bf16, float* lse, float p_drop, uint32_t seed,
+                           int min_len, void* stream);
+int nbest_attn_varlen_bwd2(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens, const uint8_t* key_valid,
+                           int B, int max_len, int heads, int T, int T_active, const void* out_bf16,
+                           const void* dout_bf16, const float* lse, void* dqkv_bf16, float* delta_ws, float p_drop,
+                           uint32_t seed, int min_len, void* stream);
+
 /* Last encoder layer: only the [CLS] row of each sequence is consumed downstream (models/model.py:46-47,58), so its
  * attention is evaluated for that single query row. out_cls [B, heads*64] bf16, lse_cls [heads, B] fp32. Same
  * arithmetic and the same dropout-mask indices as nbest_attn_varlen_fwd would use for row cu_seqlens[b]. max_len <= 512. */

@@ -47,6 +47,13 @@ _SIGNATURES = {
     "nbest_attn_varlen_fwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32, _u32, _vp]),
     "nbest_attn_varlen_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp,
                                         _f32, _u32, _vp]),
+    "nbest_attn_plan": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "nbest_attn_tiles_fwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _f32, _u32, _vp]),
+    "nbest_attn_tiles_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp,
+                                       C.c_int, _vp, _f32, _u32, _vp]),
+    "nbest_attn_varlen_fwd2": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32, _u32, C.c_int, _vp]),
+    "nbest_attn_varlen_bwd2": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp,
+                                         _f32, _u32, C.c_int, _vp]),
     "nbest_attn_cls_fwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32, _u32, _vp]),
     "nbest_attn_cls_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp,
                                      _f32, _u32, _vp]),

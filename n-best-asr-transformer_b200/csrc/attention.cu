@@ -126,11 +126,11 @@ template <int HPC>
 __global__ void __launch_bounds__(kThreads, 4)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu, const uint8_t* __restrict__ key_valid,
                 int heads, int T, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, float scale, uint32_t thr,
-                float rscale, uint32_t seed) {
+                float rscale, uint32_t seed, int min_len) {
   const int qb = blockIdx.x, h0 = blockIdx.y * HPC, b = blockIdx.z;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   const int q0 = qb * BLK;
-  if (q0 >= L) return;
+  if (q0 >= L || L < min_len) return;   // min_len = 129: shorter sequences belong to the tcgen05 tile kernel (attention_tc.cu)
   extern __shared__ __align__(128) uint8_t smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -699,9 +699,19 @@ int set_smem(nbest_ctx* ctx, K kernel, size_t bytes) {
 
 }  // namespace
 
+extern "C" int nbest_attn_varlen_fwd2(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens,
+                                      const uint8_t* key_valid, int B, int max_len, int heads, int T, void* out_bf16,
+                                      float* lse, float p_drop, uint32_t seed, int min_len, void* stream);
+
 extern "C" int nbest_attn_varlen_fwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens,
                                      const uint8_t* key_valid, int B, int max_len, int heads, int T, void* out_bf16,
                                      float* lse, float p_drop, uint32_t seed, void* stream) {
+  return nbest_attn_varlen_fwd2(ctx, qkv_bf16, cu_seqlens, key_valid, B, max_len, heads, T, out_bf16, lse, p_drop, seed, 0, stream);
+}
+
+extern "C" int nbest_attn_varlen_fwd2(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens,
+                                      const uint8_t* key_valid, int B, int max_len, int heads, int T, void* out_bf16,
+                                      float* lse, float p_drop, uint32_t seed, int min_len, void* stream) {
   if (!ctx) return NBEST_EINVAL;
   NBEST_CHECK_ARG(ctx, qkv_bf16 && cu_seqlens && out_bf16 && lse, "null pointer");
   NBEST_CHECK_ARG(ctx, B > 0 && heads > 0 && max_len > 0 && max_len <= 512, "need 0 < max_len <= 512 (BERT position limit)");
@@ -726,18 +736,31 @@ extern "C" int nbest_attn_varlen_fwd(nbest_ctx* ctx, const void* qkv_bf16, const
   }
   if (heads % 4 == 0)
     attn_fwd_kernel<4><<<dim3(nqb, heads / 4, B), kThreads, sizeof(FwdSmem), s>>>(q, cu_seqlens, key_valid, heads, T, o, lse,
-                                                                              0.125f, thr, rscale, seed);
+                                                                              0.125f, thr, rscale, seed, min_len);
   else
     attn_fwd_kernel<1><<<dim3(nqb, heads, B), kThreads, sizeof(FwdSmem), s>>>(q, cu_seqlens, key_valid, heads, T, o, lse, 0.125f,
-                                                                          thr, rscale, seed);
+                                                                          thr, rscale, seed, min_len);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
+
+extern "C" int nbest_attn_varlen_bwd2(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens,
+                                      const uint8_t* key_valid, int B, int max_len, int heads, int T, int T_active,
+                                      const void* out_bf16, const void* dout_bf16, const float* lse, void* dqkv_bf16,
+                                      float* delta_ws, float p_drop, uint32_t seed, int min_len_arg, void* stream);
 
 extern "C" int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens,
                                      const uint8_t* key_valid, int B, int max_len, int heads, int T, int T_active,
                                      const void* out_bf16, const void* dout_bf16, const float* lse, void* dqkv_bf16,
                                      float* delta_ws, float p_drop, uint32_t seed, void* stream) {
+  return nbest_attn_varlen_bwd2(ctx, qkv_bf16, cu_seqlens, key_valid, B, max_len, heads, T, T_active, out_bf16, dout_bf16, lse,
+                                dqkv_bf16, delta_ws, p_drop, seed, 0, stream);
+}
+
+extern "C" int nbest_attn_varlen_bwd2(nbest_ctx* ctx, const void* qkv_bf16, const int32_t* cu_seqlens,
+                                     const uint8_t* key_valid, int B, int max_len, int heads, int T, int T_active,
+                                      const void* out_bf16, const void* dout_bf16, const float* lse, void* dqkv_bf16,
+                                      float* delta_ws, float p_drop, uint32_t seed, int min_len_arg, void* stream) {
   if (!ctx) return NBEST_EINVAL;
   NBEST_CHECK_ARG(ctx, qkv_bf16 && cu_seqlens && dout_bf16 && lse && dqkv_bf16 && delta_ws, "null pointer");
   NBEST_CHECK_ARG(ctx, B > 0 && heads > 0 && max_len > 0 && max_len <= 512, "need 0 < max_len <= 512 (BERT position limit)");
@@ -771,8 +794,10 @@ extern "C" int nbest_attn_varlen_bwd(nbest_ctx* ctx, const void* qkv_bf16, const
   const uint32_t thr = drop_threshold(p_drop);
   const float rscale = 1.0f / (1.0f - p_drop);
   // sequences of <= 64 tokens: the fused single-tile kernel; longer ones: the dK/dV + dQ pair (skipped when there are none)
-  const bool use_fused = heads % 4 == 0 && getenv("NBEST_ATTN_NO_FUSED_BWD") == nullptr;
-  int min_len = 0;
+  // min_len_arg > 0: sequences shorter than that are handled elsewhere (attention_tc.cu takes L <= 128): only the
+  // block-loop kernels run here, on the long ones
+  const bool use_fused = heads % 4 == 0 && getenv("NBEST_ATTN_NO_FUSED_BWD") == nullptr && min_len_arg <= 0;
+  int min_len = min_len_arg > 0 ? min_len_arg : 0;
   if (use_fused) {
     static bool fattr_dev[64] = {};
     if (!fattr_dev[ctx->device & 63]) {

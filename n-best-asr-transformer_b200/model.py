@@ -154,6 +154,10 @@ class TOD_ASR_Transformer_STC(nn.Module):
         # only: ~1/12 less encoder work, identical results (with hidden dropout the compact rows draw a different, equally
         # valid mask: mask indices follow the row layout). False = run the last layer on every token.
         self.cls_only_last_layer = True
+        # Attention of sequences <= 128 tokens on the tcgen05 / TMEM / TMA tile kernels (csrc/attention_tc.cu); longer ones
+        # (10-best inference) keep the block-loop kernels of csrc/attention.cu. NBEST_ATTN_TC=0: everything on the latter.
+        import os
+        self.attn_tensor_path = os.environ.get("NBEST_ATTN_TC", "1") != "0"
         self._build_params(encoder_state, seed)
 
     # ------------------------------------------------------------------------------------------------ parameters
@@ -329,6 +333,9 @@ class TOD_ASR_Transformer_STC(nn.Module):
         pa = ops.pack_batch(input_ids, seg_ids, kind, lens)
         if trans_input_ids is None:
             pa.B_asr, pa.T_asr, pa.max_len_asr = pa.B, pa.T, pa.max_len
+            pa.sum_l2_asr = pa.sum_l2
+            if self.attn_tensor_path:
+                pa.plan = ops.attn_plan(pa.cu_seqlens, pa.seq_of, pa.B, pa.T)
             return pa
         pt = ops.pack_batch(trans_input_ids, trans_seg_ids, kind, trans_lens)
         pk = ops.Packed()
@@ -340,6 +347,8 @@ class TOD_ASR_Transformer_STC(nn.Module):
             setattr(pk, f, torch.cat([getattr(pa, f)[:pa.T], getattr(pt, f)[:pt.T]]))
         pk.seq_of = torch.cat([pa.seq_of[:pa.T], pt.seq_of[:pt.T] + pa.B])
         pk.B_asr, pk.T_asr, pk.max_len_asr = pa.B, pa.T, pa.max_len
+        pk.sum_l2, pk.sum_l2_asr = pa.sum_l2 + pt.sum_l2, pa.sum_l2
+        pk.plan = ops.attn_plan(pk.cu_seqlens, pk.seq_of, pk.B, pk.T, break_at=pa.B) if self.attn_tensor_path else None
         return pk
 
     def _seed(self, layer, site):
@@ -387,7 +396,14 @@ class TOD_ASR_Transformer_STC(nn.Module):
                 resid = x.index_select(0, pk.cu_seqlens[:pk.B].long())
             else:
                 L.lse = f32(s.heads, T)
-                ops.attn_fwd(qkv, pk.cu_seqlens, kv, pk.B, pk.max_len, s.heads, T, ctx, L.lse, p_a, self._seed(l, 1))
+                if pk.plan is not None:
+                    ops.attn_tiles_fwd(qkv, pk.plan, 0, kv, s.heads, T, ctx, L.lse, p_a, self._seed(l, 1), sum_l2=pk.sum_l2)
+                    if pk.max_len > 128:
+                        ops.attn_fwd(qkv, pk.cu_seqlens, kv, pk.B, pk.max_len, s.heads, T, ctx, L.lse, p_a, self._seed(l, 1),
+                                     min_len=129)
+                else:
+                    ops.attn_fwd(qkv, pk.cu_seqlens, kv, pk.B, pk.max_len, s.heads, T, ctx, L.lse, p_a, self._seed(l, 1),
+                                 sum_l2=pk.sum_l2)
                 resid = x
             ops.gemm(ctx, w["h_wo"], epilogue=ops.EPI_BIAS_DROP_RES, bias=w["p_bo"], aux=resid, out=pre1, p_drop=p_h,
                      seed=self._seed(l, 2))
@@ -477,8 +493,16 @@ class TOD_ASR_Transformer_STC(nn.Module):
                 dres.index_copy_(0, cu[:B_act].long(), dpre)
                 dx = bf(T_act, H)
             else:
-                ops.attn_bwd(L.qkv, cu, kv, B_act, max_len, s.heads, T, None, dctx, L.lse, dqkv, delta, p_a, self._seed(l, 1),
-                             T_active=T_act)
+                l2s = pk.sum_l2 if B_act == pk.B else pk.sum_l2_asr
+                if pk.plan is not None:
+                    ops.attn_tiles_bwd(L.qkv, pk.plan, 0 if B_act == pk.B else 1, kv, s.heads, T, T_act, dctx, L.lse, delta, T_act,
+                                       dqkv, p_a, self._seed(l, 1), sum_l2=l2s)
+                    if max_len > 128:
+                        ops.attn_bwd(L.qkv, cu, kv, B_act, max_len, s.heads, T, None, dctx, L.lse, dqkv, delta, p_a,
+                                     self._seed(l, 1), T_active=T_act, min_len=129)
+                else:
+                    ops.attn_bwd(L.qkv, cu, kv, B_act, max_len, s.heads, T, None, dctx, L.lse, dqkv, delta, p_a, self._seed(l, 1),
+                                 T_active=T_act, sum_l2=l2s)
                 dres = dpre
             ops.gemm(dqkv, w["h_wqkv"], b_mn_major=True, epilogue=ops.EPI_ADD, aux=dres, out=dx)   # (full path: dx was consumed above)
             ops.gemm(dqkv, A(L.x_in), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_wqkv"])

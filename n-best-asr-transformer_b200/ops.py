@@ -271,20 +271,78 @@ def cast_f32_bf16(src, dst):
 
 
 # ---------------------------------------------------------------------------------------------------------- attention
-def attn_fwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out, lse, p_drop=0.0, seed=0):
+def _attn_cost(T, sum_l2, heads, bwd=False, T_active=None):
+    """Algorithmic FLOPs / bytes of one attention call: forward 4 * L^2 * 64 per (sequence, head), backward
+    twice that; bytes = QKV rows read + context rows written (+ dO read, dQKV written in the backward) + lse / delta."""
+    hd = heads * 64
+    Ta = T if T_active is None else T_active
+    fl = 4.0 * sum_l2 * hd * (2.0 if bwd else 1.0)
+    by = (Ta * (3 * hd + hd + 3 * hd) * 2.0 + 2 * heads * Ta * 4.0) if bwd else (T * (3 * hd + hd) * 2.0 + heads * T * 4.0)
+    return fl, by
+
+
+def attn_fwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out, lse, p_drop=0.0, seed=0, min_len=0, sum_l2=0.0):
+    """min_len > 0: only sequences of at least that many tokens (the rest belongs to attn_tiles_fwd)."""
     ctx = _ctx(qkv)
-    with _Timed('attn_varlen_fwd', 0.0, 0.0):
-        ctx.check(_lib.lib().nbest_attn_varlen_fwd(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
-                                                   _p(out), _p(lse), float(p_drop), _seed(seed), _stream()))
+    fl, by = _attn_cost(T, sum_l2, heads) if (sum_l2 and not min_len) else (0.0, 0.0)
+    with _Timed('attn_varlen_fwd', fl, by):
+        ctx.check(_lib.lib().nbest_attn_varlen_fwd2(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
+                                                    _p(out), _p(lse), float(p_drop), _seed(seed), int(min_len), _stream()))
 
 
 def attn_bwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out, dout, lse, dqkv, delta_ws, p_drop=0.0, seed=0,
-             T_active=None):
+             T_active=None, min_len=0, sum_l2=0.0):
     ctx = _ctx(qkv)
-    with _Timed('attn_varlen_bwd', 0.0, 0.0):
-        ctx.check(_lib.lib().nbest_attn_varlen_bwd(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
-                                                   T if T_active is None else T_active, _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta_ws), float(p_drop), _seed(seed),
-                                                   _stream()))
+    fl, by = _attn_cost(T, sum_l2, heads, True, T_active) if (sum_l2 and not min_len) else (0.0, 0.0)
+    with _Timed('attn_varlen_bwd', fl, by):
+        ctx.check(_lib.lib().nbest_attn_varlen_bwd2(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
+                                                    T if T_active is None else T_active, _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta_ws), float(p_drop), _seed(seed),
+                                                    int(min_len), _stream()))
+
+
+class AttnPlan:
+    """Tile plan of a packed batch for the tcgen05 attention kernels (see nbest_attn_plan)."""
+    __slots__ = ("tiles", "counts", "row_bounds", "max_tiles")
+
+
+def attn_plan(cu_seqlens, seq_of, B, T, break_at=None):
+    """Greedy packing of the batch's sequences (<= 128 tokens each) into 128-row tiles + per-token sequence bounds.
+    break_at: no tile straddles this sequence index (the ASR / transcript boundary of the merged batch)."""
+    dev = cu_seqlens.device
+    pl = AttnPlan()
+    pl.tiles = torch.empty(2 * B, dtype=torch.int32, device=dev)
+    pl.counts = torch.empty(4, dtype=torch.int32, device=dev)
+    pl.row_bounds = torch.empty(2 * max(T, 1), dtype=torch.int32, device=dev)
+    pl.max_tiles = B
+    ctx = _ctx(cu_seqlens)
+    with _Timed('attn_plan', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_attn_plan(ctx.handle, _p(cu_seqlens), _p(seq_of), B, T, B if break_at is None else break_at,
+                                             _p(pl.tiles), _p(pl.counts), _p(pl.row_bounds), _stream()))
+    return pl
+
+
+def attn_tiles_fwd(qkv, plan, count_idx, key_valid, heads, T, out, lse, p_drop=0.0, seed=0, sum_l2=0.0):
+    """tcgen05 / TMEM / TMA attention forward over the plan's tiles (sequences of <= 128 tokens)."""
+    ctx = _ctx(qkv)
+    _check_bf16(qkv, "qkv")
+    fl, by = _attn_cost(T, sum_l2, heads) if sum_l2 else (0.0, 0.0)
+    with _Timed('attn_tiles_fwd', fl, by):
+        ctx.check(_lib.lib().nbest_attn_tiles_fwd(ctx.handle, _p(qkv), _p(plan.tiles), _p(plan.counts), int(count_idx),
+                                                  plan.max_tiles, _p(plan.row_bounds), _p(key_valid), heads, T, _p(out), _p(lse),
+                                                  float(p_drop), _seed(seed), _stream()))
+
+
+def attn_tiles_bwd(qkv, plan, count_idx, key_valid, heads, T, T_active, dout, lse, delta, delta_pitch, dqkv, p_drop=0.0, seed=0,
+                   sum_l2=0.0):
+    ctx = _ctx(qkv)
+    _check_bf16(qkv, "qkv")
+    _check_bf16(dout, "dout")
+    fl, by = _attn_cost(T, sum_l2, heads, True, T_active) if sum_l2 else (0.0, 0.0)
+    with _Timed('attn_tiles_bwd', fl, by):
+        ctx.check(_lib.lib().nbest_attn_tiles_bwd(ctx.handle, _p(qkv), _p(plan.tiles), _p(plan.counts), int(count_idx),
+                                                  plan.max_tiles, _p(plan.row_bounds), _p(key_valid), heads, T, T_active, _p(dout),
+                                                  _p(lse), _p(delta), int(delta_pitch), _p(dqkv), float(p_drop), _seed(seed),
+                                                  _stream()))
 
 
 def attn_cls_fwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out_cls, lse_cls, p_drop=0.0, seed=0):

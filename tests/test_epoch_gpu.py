@@ -110,7 +110,8 @@ def test_eval_epoch_matches_oracle_forward_and_reference_metric_code():
     model, optim, opt, memory, meta, raw_in, raw_trans, cfg, params, hier = _setup()
     data = _batches(E, meta, raw_in, raw_trans, 16)
     fp = io.StringIO()
-    mean_loss, (p, r, f), acc, cases = E.eval_epoch(model, data, opt, memory, fp=fp)
+    mean_loss, (p, r, f), acc, eic = E.eval_epoch(model, data, opt, memory, fp=fp)
+    cases = list(zip([x.split(" ") for x in eic.raw_inputs], eic.whole_pred_classes, eic.true_golds))
     assert len(cases) == 48 and fp.getvalue().count("\n") == 48
     # oracle, batch by batch
     losses, tp, fpn, fn, corr = [], 0, 0, 0, 0

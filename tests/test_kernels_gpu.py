@@ -570,3 +570,129 @@ def test_bertadam_matches_oracle_trajectory():
     assert torch.equal(flat_b, flat_p.to(torch.bfloat16))
     pool = flat_p[offsets[2]:offsets[2] + 64 * 64].cpu().view(64, 64)
     assert torch.equal(pool, params["bert_encoder.pooler.dense.weight"])      # grad None -> never touched
+
+
+# ------------------------------------------------------------------------------------------- attention, tcgen05 tile path
+def _tiles_setup(lens, seed=0, xlmr_mask=True):
+    from nbest_b200 import ops
+    heads, B = 12, len(lens)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    T = int(cu[-1])
+    g = torch.Generator(device="cuda").manual_seed(seed + sum(lens))
+    qkv = (torch.randn(T, 3 * heads * 64, device="cuda", generator=g) * 1.2).to(torch.bfloat16)
+    key_valid = torch.ones(T, dtype=torch.uint8, device="cuda")
+    if xlmr_mask:
+        for b in range(B):
+            if lens[b] > 4:
+                key_valid[int(cu[b])] = 0 if b % 2 else 1
+                key_valid[int(cu[b]) + 3] = 0
+    cu_d = torch.from_numpy(cu).cuda()
+    seq_of = torch.repeat_interleave(torch.arange(B, dtype=torch.int32), torch.tensor(lens)).cuda()
+    dout = torch.randn(T, heads * 64, device="cuda", generator=g).to(torch.bfloat16)
+    return ops, heads, B, cu, cu_d, T, qkv, key_valid, seq_of, dout
+
+
+@pytest.mark.parametrize("lens", [[1, 17, 64, 65, 128], [46] * 9, [128, 128, 1, 127, 2, 90, 38], [200, 3, 512, 129, 77, 128, 5],
+                                  list(range(20, 77, 3)) * 3])
+def test_attention_tile_kernels_match_reference_and_block_kernels(lens):
+    """tcgen05 tile path (sequences <= 128 tokens packed into 128-row tiles, block-diagonal mask) + block-loop kernels for
+    the longer ones == fp32 reference; the plan is checked against a host restatement of the greedy packing."""
+    ops, heads, B, cu, cu_d, T, qkv, key_valid, seq_of, dout = _tiles_setup(lens)
+    br = B // 2
+    plan = ops.attn_plan(cu_d, seq_of, B, T, break_at=br)
+    tiles, counts = plan.tiles.cpu().numpy().reshape(-1, 2), plan.counts.cpu().numpy()
+    exp, start, rows, n_break = [], -1, 0, None
+    for b in range(B + 1):
+        if b == br and n_break is None:
+            if start >= 0:
+                exp.append((start, rows))
+            start, rows, n_break = -1, 0, len(exp)
+        if b == B:
+            break
+        L = lens[b]
+        if L > 128:
+            if start >= 0:
+                exp.append((start, rows))
+            start, rows = -1, 0
+            continue
+        if start >= 0 and rows + L > 128:
+            exp.append((start, rows))
+            start, rows = -1, 0
+        if start < 0:
+            start = int(cu[b])
+        rows += L
+    if start >= 0:
+        exp.append((start, rows))
+    assert counts[0] == len(exp) and counts[1] == n_break and counts[2] == sum(l > 128 for l in lens)
+    assert [tuple(x) for x in tiles[:len(exp)]] == exp
+    rb = plan.row_bounds.cpu().numpy().reshape(-1, 2)[:T]
+    assert np.array_equal(rb[:, 0], cu[seq_of.cpu().numpy()]) and np.array_equal(rb[:, 1], cu[seq_of.cpu().numpy() + 1])
+
+    for kv in (key_valid, None):
+        out = torch.zeros(T, heads * 64, device="cuda", dtype=torch.bfloat16)
+        lse = torch.zeros(heads, T, device="cuda")
+        ops.attn_tiles_fwd(qkv, plan, 0, kv, heads, T, out, lse)
+        if max(lens) > 128:
+            ops.attn_fwd(qkv, cu_d, kv, B, max(lens), heads, T, out, lse, min_len=129)
+        kvr = key_valid if kv is not None else torch.ones_like(key_valid)
+        ref_out, ref_grads = _attn_ref(qkv, cu, kvr, heads, dout)
+        assert _rel(out, ref_out) < 1e-2
+        out_b = torch.empty_like(out)
+        lse_b = torch.empty_like(lse)
+        ops.attn_fwd(qkv, cu_d, kv, B, max(lens), heads, T, out_b, lse_b)
+        assert _rel(lse, lse_b) < 2e-3
+        delta = (dout.float() * out.float()).view(T, heads, 64).sum(-1).t().contiguous()
+        dqkv = torch.zeros_like(qkv)
+        ops.attn_tiles_bwd(qkv, plan, 0, kv, heads, T, T, dout, lse, delta, T, dqkv)
+        if max(lens) > 128:
+            ops.attn_bwd(qkv, cu_d, kv, B, max(lens), heads, T, None, dout, lse, dqkv, delta, min_len=129)
+        assert _rel(dqkv, ref_grads) < 2e-2 and _cos(dqkv, ref_grads) > 0.9995
+    # gradient-carrying prefix only (count_idx = 1, T_active = rows of the first `br` sequences): rows beyond stay untouched
+    Ta = int(cu[br])
+    if Ta > 0:
+        dq2 = torch.full_like(qkv, 7.0)[:Ta].contiguous()
+        ops.attn_tiles_bwd(qkv, plan, 1, None, heads, T, Ta, dout[:Ta].contiguous(), lse, delta[:, :Ta].contiguous(), Ta, dq2)
+        short = torch.tensor([lens[int(s)] <= 128 for s in seq_of[:Ta].cpu()])
+        assert _rel(dq2[short.cuda()], dqkv[:Ta][short.cuda()]) < 2e-3
+        assert bool((dq2[~short.cuda()] == 7.0).all())
+
+
+def test_attention_tile_kernels_dropout_masks_are_the_shared_index_map():
+    """Dropout of the tile path: (a) bit-exact against the oracle restatement of the hash for sequences that start at
+    arbitrary tile columns (the per-row keep bits are shifted into column space), (b) forward and backward agree with the
+    block-loop kernels on the same seed (same masks => same results up to bf16 rounding)."""
+    from oracle import stc_oracle as O
+    lens = [40, 33, 50, 64, 17, 128, 100]
+    ops, heads, B, cu, cu_d, T, qkv, key_valid, seq_of, dout = _tiles_setup(lens, seed=3, xlmr_mask=False)
+    plan = ops.attn_plan(cu_d, seq_of, B, T)
+    pa, seed = 0.25, 99
+    # (a) V = e_j probes: O[q, j] = P_drop[q, j] for sequences of <= 64 tokens
+    probe = qkv.clone()
+    probe[:, :2 * heads * 64] = 0                                    # uniform scores: P = 1/L before dropout
+    v = torch.zeros(T, 64)
+    for b in range(B):
+        for j in range(min(lens[b], 64)):
+            v[int(cu[b]) + j, j] = 1.0
+    probe[:, 2 * heads * 64:] = v.repeat(1, heads).to(torch.bfloat16).cuda()
+    out = torch.zeros(T, heads * 64, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(heads, T, device="cuda")
+    ops.attn_tiles_fwd(probe, plan, 0, None, heads, T, out, lse, p_drop=pa, seed=seed)
+    got = out.float().cpu().view(T, heads, 64) != 0
+    for b in range(B):
+        L = lens[b]
+        if L > 64:
+            continue
+        for tq in range(int(cu[b]), int(cu[b + 1])):
+            keep = O.attn_dropout_keep_mask(seed, heads, T, tq, L, pa)              # [heads, L]
+            assert np.array_equal(got[tq, :, :L].numpy(), keep), (b, tq)
+    # (b) against the block-loop kernels
+    out_a, out_b = torch.zeros_like(out), torch.zeros_like(out)
+    lse_a, lse_b = torch.zeros_like(lse), torch.zeros_like(lse)
+    ops.attn_tiles_fwd(qkv, plan, 0, key_valid, heads, T, out_a, lse_a, p_drop=pa, seed=seed)
+    ops.attn_fwd(qkv, cu_d, key_valid, B, max(lens), heads, T, out_b, lse_b, p_drop=pa, seed=seed)
+    assert _rel(out_a, out_b) < 1e-2 and _rel(lse_a, lse_b) < 2e-3
+    delta = (dout.float() * out_b.float()).view(T, heads, 64).sum(-1).t().contiguous()
+    dq_a, dq_b = torch.zeros_like(qkv), torch.zeros_like(qkv)
+    ops.attn_tiles_bwd(qkv, plan, 0, key_valid, heads, T, T, dout, lse_b, delta, T, dq_a, p_drop=pa, seed=seed)
+    ops.attn_bwd(qkv, cu_d, key_valid, B, max(lens), heads, T, None, dout, lse_b, dq_b, delta, p_drop=pa, seed=seed)
+    assert _rel(dq_a, dq_b) < 1e-2 and _cos(dq_a, dq_b) > 0.9999

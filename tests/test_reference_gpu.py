@@ -190,8 +190,11 @@ def test_reference_train_epoch_stock_vs_swapped_imports_vs_fused_mirror(n_accum)
             # 96 utterances, ~130 gold labels: a label flipping at the 0.5 threshold moves P/R/F by < 1 point
             assert abs(p1 - p0) <= 2.5 and abs(r1 - r0) <= 2.5 and abs(f1 - f0) <= 2.5, (mode, ep, (p0, r0, f0), (p1, r1, f1))
             assert abs(a1 - a0) <= 100.0 * 2 / 96 + 1e-9, (mode, ep, a0, a1)
-    # the second epoch really trained (the loss moved) and all three agree on by how much
-    assert results["stock"][1][0] < results["stock"][0][0]
+    # the optimizer steps are visible in the second epoch (the loss moved by far more than fp32 noise), so the
+    # epoch-2 agreement above covers BertAdam / warm-up / accumulation, not just the forward pass
+    moved = abs(results["stock"][1][0] - results["stock"][0][0]) / abs(results["stock"][0][0])
+    print("train_epoch loss epoch0 -> epoch1:", {m: (round(r[0][0], 4), round(r[1][0], 4)) for m, r in results.items()})
+    assert moved > 1e-3, moved
 
 
 def test_eval_epoch_return_contract_and_values_vs_reference():
