@@ -21,15 +21,30 @@ def run(lens, name, bwd=True, reps=30):
     dqkv = torch.empty_like(qkvs[0]); delta = torch.empty(heads, T, device="cuda")
     def f(i): ops.attn_fwd(qkvs[i % 3], cu_d, None, B, int(max(lens)), heads, T, out, lse, p_drop=0.1, seed=i)
     def bw(i): ops.attn_bwd(qkvs[i % 3], cu_d, None, B, int(max(lens)), heads, T, out, dout, lse, dqkv, delta, p_drop=0.1, seed=i)
+    seq_of = torch.repeat_interleave(torch.arange(B, dtype=torch.int32), torch.from_numpy(np.asarray(lens)).long()).cuda()
+    plan = ops.attn_plan(cu_d, seq_of, B, T)
+    long_ = int(max(lens)) > 128
+    def ft(i):
+        ops.attn_tiles_fwd(qkvs[i % 3], plan, 0, None, heads, T, out, lse, p_drop=0.1, seed=i)
+        if long_: ops.attn_fwd(qkvs[i % 3], cu_d, None, B, int(max(lens)), heads, T, out, lse, p_drop=0.1, seed=i, min_len=129)
+    def bt(i):
+        ops.attn_tiles_bwd(qkvs[i % 3], plan, 0, None, heads, T, T, dout, lse, delta, T, dqkv, p_drop=0.1, seed=i)
+        if long_: ops.attn_bwd(qkvs[i % 3], cu_d, None, B, int(max(lens)), heads, T, None, dout, lse, dqkv, delta, p_drop=0.1, seed=i, min_len=129)
     res = []
-    for fn in ([f, bw] if bwd else [f]):
+    for fn in ([f, bw, ft, bt] if bwd else [f, ft]):
         for i in range(3): fn(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(reps): fn(i)
         e1.record(); torch.cuda.synchronize()
         res.append(e0.elapsed_time(e1) / reps * 1e3)
-    print("%-28s B=%4d T=%6d max=%3d  fwd %7.1f us%s" % (name, B, T, max(lens), res[0], ("  bwd %7.1f us" % res[1]) if bwd else ""))
+    hbm_f, hbm_b = T * 768 * 2 * 4 / 6545.6e3, T * 768 * 2 * 7 / 6545.6e3      # us at the measured HBM peak
+    if bwd:
+        print("%-28s B=%4d T=%6d max=%3d  mma.sync fwd %7.1f bwd %7.1f us | tcgen05 tiles fwd %7.1f bwd %7.1f us | HBM floor %5.1f / %5.1f us (n_tiles %d)" % (
+            name, B, T, max(lens), res[0], res[1], res[2], res[3], hbm_f, hbm_b, int(plan.counts[0])))
+    else:
+        print("%-28s B=%4d T=%6d max=%3d  mma.sync fwd %7.1f us | tcgen05 tiles fwd %7.1f us | HBM floor %5.1f us (n_tiles %d)" % (
+            name, B, T, max(lens), res[0], res[1], hbm_f, int(plan.counts[0])))
 
 run(np.concatenate([la, lt]), "fwd shape (asr+transcript)", bwd=False)
 run(la, "bwd shape (asr only)")
