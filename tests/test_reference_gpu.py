@@ -207,6 +207,10 @@ def test_eval_epoch_return_contract_and_values_vs_reference():
     enc = R.hf_encoder("bert", num_hidden_layers=2)
     opt = R.make_opt(enc, mem, "cuda", pre_trained_model="bert", dropout=0.3, tokenizer=FakeTok())
     theirs = ref.make_model(opt).to("cuda")
+    with torch.no_grad():      # spread the head's logits: a default-init head puts every act-slot score within bf16 noise of 0.5
+        for n, p in theirs.clf.named_parameters():
+            if n.endswith("weight"):
+                p.mul_(30.0)
     ours = our_make_model(opt)
     ours.load_state_dict({k: v for k, v in theirs.state_dict().items() if k.startswith("clf.")}, strict=False)
     data = _epoch_data(ref, R, mem, 64, 16, torch.device("cuda"))
@@ -215,7 +219,7 @@ def test_eval_epoch_return_contract_and_values_vs_reference():
         ra = ref.nb.eval_epoch(theirs, data, opt, mem, fa, ea)
     rb = E.eval_epoch(ours, data, opt, mem, fb, eb)
     assert len(ra) == len(rb) == 4
-    assert abs(rb[0] - ra[0]) <= 1e-2 * abs(ra[0])
+    assert abs(rb[0] - ra[0]) <= 2e-2 * abs(ra[0]), (ra[0], rb[0])
     la, lb = fa.getvalue().split("\n"), fb.getvalue().split("\n")
     assert len(la) == len(lb) == 65
     # same dump format, same inputs / golds; with random-init weights the top scores sit near 0.5, so a few of the ~30
