@@ -43,6 +43,12 @@ void nbest_ctx_destroy(nbest_ctx* ctx);
 const char* nbest_last_error(nbest_ctx* ctx);
 /* Number of kernels launched through ctx so far (bench.py's gpu_launches). */
 uint64_t nbest_launch_count(nbest_ctx* ctx);
+/* The persistent GEMMs size their grids to (SM count - n_sms): the data-parallel trainer reserves SMs while a gradient
+ * all-reduce is in flight so that NCCL's CTAs and the statically scheduled CTA pairs do not wait for each other
+ * (replaces nothing in the reference: it has no multi-GPU path, utils/gpu_selection.py:27-66 picks ONE device). */
+int nbest_ctx_set_sm_reserve(nbest_ctx* ctx, int n_sms);
+/* TMA descriptor cache hits so far (host-overhead diagnostics). */
+uint64_t nbest_tmap_cache_hits(nbest_ctx* ctx);
 
 /* ---- A2: packed variable-length batch layout ------------------------------------------------------------- */
 /* Replaces the padded tensors of utils/bert_xlnet_inputs.py:91-102 plus `attention_mask = input_ids > 0`
@@ -265,7 +271,9 @@ typedef struct {
   int32_t active;   /* 0: grad is None in the reference (pooler) -> skipped entirely */
 } nbest_adam_tensor;
 /* chunks[] (device, int32 triples {tensor, start, len}) tile the active tensors; start is relative to the tensor.
- * norms_ws[n_tensors] fp32 scratch. sched = schedule.get_lr(step) computed by the host in double.
+ * norms_ws[n_tensors + n_chunks] fp32 scratch (per-tensor sums of squares, then the per-chunk partials they are folded
+ * from in a fixed order: replicas fed identical gradients stay bit-identical). sched = schedule.get_lr(step) computed by
+ * the host in double.
  * p_bf16 (nullable) receives the refreshed bf16 working copy of p. grad_scale multiplies g before use (1/R etc). */
 int nbest_bertadam_step(nbest_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16,
                         const nbest_adam_tensor* tensors, int n_tensors, const int32_t* chunks, int n_chunks,

@@ -32,6 +32,8 @@ _SIGNATURES = {
     "nbest_ctx_destroy": (None, [_vp]),
     "nbest_last_error": (C.c_char_p, [_vp]),
     "nbest_launch_count": (_u64, [_vp]),
+    "nbest_ctx_set_sm_reserve": (C.c_int, [_vp, C.c_int]),
+    "nbest_tmap_cache_hits": (_u64, [_vp]),
     "nbest_pack_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nbest_pack_hyp_ids": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "nbest_embed_ln_fwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _f32, C.c_int, _vp, _vp, _vp,
@@ -130,6 +132,12 @@ class Context:
 
     def launches(self):
         return int(self._l.nbest_launch_count(self.handle))
+
+    def set_sm_reserve(self, n_sms):
+        self.check(self._l.nbest_ctx_set_sm_reserve(self.handle, int(n_sms)))
+
+    def tmap_cache_hits(self):
+        return int(self._l.nbest_tmap_cache_hits(self.handle))
 
     def __del__(self):
         try:

@@ -796,7 +796,7 @@ extern "C" int nbest_attn_varlen_bwd2(nbest_ctx* ctx, const void* qkv_bf16, cons
   // sequences of <= 64 tokens: the fused single-tile kernel; longer ones: the dK/dV + dQ pair (skipped when there are none)
   // min_len_arg > 0: sequences shorter than that are handled elsewhere (attention_tc.cu takes L <= 128): only the
   // block-loop kernels run here, on the long ones
-  const bool use_fused = heads % 4 == 0 && getenv("NBEST_ATTN_NO_FUSED_BWD") == nullptr && min_len_arg <= 0;
+  const bool use_fused = heads % 4 == 0 && !ctx->knobs.attn_no_fused_bwd && min_len_arg <= 0;
   int min_len = min_len_arg > 0 ? min_len_arg : 0;
   if (use_fused) {
     static bool fattr_dev[64] = {};

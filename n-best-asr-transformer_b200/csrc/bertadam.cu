@@ -6,6 +6,9 @@
 // correction. The reference launches ~14 kernels per tensor (~3 k per step); here it is two launches per step:
 //   pass 1: per-tensor sum of squares of the gradient                       (reads g:           4 B / param)
 //   pass 2: clip + moments + decay + update (+ bf16 working copy refresh)   (reads p,g,m,v, writes p,m,v[,bf16]: 28-30 B)
+// The norm is reduced in a FIXED order (per-chunk partials, then one block per tensor folds its partials): data-parallel
+// replicas that received bit-identical all-reduced gradients compute bit-identical clip coefficients and stay
+// bit-identical (an atomicAdd reduction made them drift apart by ~1e-7 per step; tests/dp_parity_2gpu.py).
 #include <math.h>
 
 #include "common.h"
@@ -19,7 +22,7 @@ constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads)
 adam_norm_kernel(const float* __restrict__ g, const nbest_adam_tensor* __restrict__ tensors, const int32_t* __restrict__ chunks,
-                 float* __restrict__ norms) {
+                 float* __restrict__ partials) {
   const int ti = chunks[3 * blockIdx.x], start = chunks[3 * blockIdx.x + 1], len = chunks[3 * blockIdx.x + 2];
   const int64_t base = tensors[ti].offset + start;
   const float* gp = g + base;
@@ -37,7 +40,38 @@ adam_norm_kernel(const float* __restrict__ g, const nbest_adam_tensor* __restric
   if (threadIdx.x < 32) {
     float v = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(norms + ti, v);
+    if (threadIdx.x == 0) partials[blockIdx.x] = v;      // fixed-order reduction: no atomics
+  }
+}
+
+// norms[ti] = sum of the chunk partials of tensor ti, folded in a fixed order (one block per tensor; chunks are sorted by
+// tensor, so the tensor's range is found by bisection)
+__global__ void __launch_bounds__(kThreads)
+adam_norm_finish_kernel(const int32_t* __restrict__ chunks, int n_chunks, const float* __restrict__ partials,
+                        float* __restrict__ norms) {
+  const int ti = blockIdx.x;
+  int lo = 0, hi = n_chunks;
+  while (lo < hi) {                      // first chunk with tensor index >= ti
+    const int mid = (lo + hi) >> 1;
+    if (chunks[3 * mid] < ti) lo = mid + 1; else hi = mid;
+  }
+  const int first = lo;
+  hi = n_chunks;
+  while (lo < hi) {                      // first chunk with tensor index > ti
+    const int mid = (lo + hi) >> 1;
+    if (chunks[3 * mid] <= ti) lo = mid + 1; else hi = mid;
+  }
+  const int last = lo;
+  float acc = 0.f;
+  for (int i = first + threadIdx.x; i < last; i += kThreads) acc += partials[i];
+  acc = warp_sum(acc);
+  __shared__ float sh[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) norms[ti] = v;
   }
 }
 
@@ -80,14 +114,15 @@ adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
     if (global_clip) {
       // torch.nn.utils.clip_grad_norm_ over ALL parameters (n_best_asr_bert.py:268-271): the 2-norm of the per-tensor
       // norms; every block folds the <= few hundred partial sums itself (inactive tensors hold 0)
-      __shared__ float tot;
+      __shared__ float wsum[kThreads / 32];
       float a = 0.f;
       for (int i = threadIdx.x; i < n_tensors; i += kThreads) a += norms[i];
       a = warp_sum(a);
-      if (threadIdx.x == 0) tot = 0.f;
+      if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = a;
       __syncthreads();
-      if ((threadIdx.x & 31) == 0) atomicAdd(&tot, a);
-      __syncthreads();
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) tot += wsum[w];     // same order in every block and on every rank
       sq = tot;
     }
     coef = fminf(max_grad_norm / (sqrtf(sq) + 1e-6f), 1.0f);   // clip_grad_norm_: clamp(max_norm / (norm + 1e-6), max=1)
@@ -134,8 +169,9 @@ extern "C" int nbest_adam_step(nbest_ctx* ctx, int mode, float* p, const float* 
                          reinterpret_cast<uintptr_t>(v)) & 15) == 0, "flat buffers must be 16-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (max_grad_norm > 0.f) {
-    NBEST_CHECK_CUDA(ctx, cudaMemsetAsync(norms_ws, 0, sizeof(float) * n_tensors, s));
-    adam_norm_kernel<<<n_chunks, kThreads, 0, s>>>(g, tensors, chunks, norms_ws);
+    adam_norm_kernel<<<n_chunks, kThreads, 0, s>>>(g, tensors, chunks, norms_ws + n_tensors);
+    NBEST_CHECK_LAUNCH(ctx);
+    adam_norm_finish_kernel<<<n_tensors, kThreads, 0, s>>>(chunks, n_chunks, norms_ws + n_tensors, norms_ws);
     NBEST_CHECK_LAUNCH(ctx);
   }
   float inv_bc1 = 1.f, inv_sqrt_bc2 = 1.f;

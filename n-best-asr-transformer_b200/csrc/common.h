@@ -12,12 +12,37 @@ typedef CUresult (*nbest_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuu
                                           const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                           CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// Environment knobs, read ONCE at nbest_ctx_create (a getenv per GEMM launch showed up in the host profile).
+struct nbest_knobs {
+  int gemm_cta_group;   // NBEST_GEMM_CTA_GROUP: 1 = single-CTA tiles, else CTA pairs
+  int gemm_force_bn;    // NBEST_GEMM_BN: 128 / 256, 0 = automatic
+  int wgrad_splits;     // NBEST_WGRAD_SPLITS: >= 1 forces the split count, 0 = automatic
+  int gemm_debug;       // NBEST_GEMM_DEBUG
+  int gemm_stages;      // NBEST_GEMM_STAGES: cap on the smem ring depth, 0 = full
+  int attn_no_fused_bwd;   // NBEST_ATTN_NO_FUSED_BWD
+};
+
+// A tensor map is a pure function of (base, rows, cols, pitch, box): the caching allocator hands the same buffers back
+// every step, so encoded maps are kept in a small direct-mapped cache instead of calling the driver 3-4 times per GEMM.
+struct nbest_tmap_entry {
+  const void* base;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows;
+  uint32_t valid;
+  CUtensorMap map;
+};
+constexpr int kTmapCacheSize = 1024;
+
 struct nbest_ctx {
   int device;
   int num_sms;
   int cc_major, cc_minor;
   nbest_encode_tiled_fn encode_tiled;  // resolved through cudaGetDriverEntryPoint (no link-time libcuda dependency)
   uint64_t launches;                   // kernels launched through this context (bench.py reports it)
+  nbest_knobs knobs;
+  int reserve_sms;                     // SMs the persistent GEMMs leave free (nbest_ctx_set_sm_reserve)
+  uint64_t tmap_hits, tmap_misses;
+  nbest_tmap_entry* tmap_cache;
   char err[512];
 };
 

@@ -53,12 +53,39 @@ extern "C" int nbest_ctx_create(nbest_ctx** out, int device) {
     return NBEST_ECUDA;
   }
   ctx->encode_tiled = (nbest_encode_tiled_fn)fn;
+  auto env_int = [](const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+  };
+  ctx->knobs.gemm_cta_group = env_int("NBEST_GEMM_CTA_GROUP", 2) == 1 ? 1 : 2;
+  ctx->knobs.gemm_force_bn = env_int("NBEST_GEMM_BN", 0);
+  ctx->knobs.wgrad_splits = env_int("NBEST_WGRAD_SPLITS", 0);
+  ctx->knobs.gemm_debug = env_int("NBEST_GEMM_DEBUG", 0);
+  ctx->knobs.gemm_stages = env_int("NBEST_GEMM_STAGES", 0);
+  ctx->knobs.attn_no_fused_bwd = getenv("NBEST_ATTN_NO_FUSED_BWD") != nullptr;
+  ctx->reserve_sms = env_int("NBEST_GEMM_RESERVE_SMS", 0);
+  ctx->tmap_cache = (nbest_tmap_entry*)calloc(kTmapCacheSize, sizeof(nbest_tmap_entry));
+  if (!ctx->tmap_cache) {
+    free(ctx);
+    return NBEST_EINVAL;
+  }
   ctx->err[0] = 0;
   *out = ctx;
   return NBEST_OK;
 }
 
-extern "C" void nbest_ctx_destroy(nbest_ctx* ctx) { free(ctx); }
+extern "C" void nbest_ctx_destroy(nbest_ctx* ctx) {
+  if (ctx) free(ctx->tmap_cache);
+  free(ctx);
+}
+
+extern "C" int nbest_ctx_set_sm_reserve(nbest_ctx* ctx, int n_sms) {
+  if (!ctx || n_sms < 0 || n_sms > ctx->num_sms - 2) return NBEST_EINVAL;
+  ctx->reserve_sms = n_sms & ~1;      // CTA pairs: whole TPCs
+  return NBEST_OK;
+}
+
+extern "C" uint64_t nbest_tmap_cache_hits(nbest_ctx* ctx) { return ctx ? ctx->tmap_hits : 0; }
 
 extern "C" const char* nbest_last_error(nbest_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
 
@@ -74,6 +101,16 @@ int nbest_make_tmap_bf16(nbest_ctx* ctx, CUtensorMap* out, const void* base, uin
     nbest_set_error(ctx, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
     return NBEST_EINVAL;
   }
+  uint64_t h = reinterpret_cast<uintptr_t>(base) * 0x9E3779B97F4A7C15ull;
+  h ^= (rows + 0x632BE59BD9B4E019ull) * 0xC2B2AE3D27D4EB4Full;
+  h ^= (cols * 0x165667B19E3779F9ull) ^ (ld * 0x27D4EB2F165667C5ull) ^ ((uint64_t)box_rows << 48);
+  nbest_tmap_entry* e = &ctx->tmap_cache[(h ^ (h >> 29)) & (kTmapCacheSize - 1)];
+  if (e->valid && e->base == base && e->rows == rows && e->cols == cols && e->ld == ld && e->box_rows == box_rows) {
+    *out = e->map;
+    ++ctx->tmap_hits;
+    return NBEST_OK;
+  }
+  ++ctx->tmap_misses;
   CUresult r = ctx->encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -82,5 +119,12 @@ int nbest_make_tmap_bf16(nbest_ctx* ctx, CUtensorMap* out, const void* base, uin
                     (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
     return NBEST_ECUDA;
   }
+  e->base = base;
+  e->rows = rows;
+  e->cols = cols;
+  e->ld = ld;
+  e->box_rows = box_rows;
+  e->map = *out;
+  e->valid = 1;
   return NBEST_OK;
 }

@@ -474,7 +474,9 @@ int launch(nbest_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const
     }
   }
   const int num_work = g.num_m_tiles * g.num_n_tiles * g.num_splits;
-  const int units = num_work < max_units ? num_work : max_units;
+  int avail = max_units - ctx->reserve_sms / CG;
+  if (avail < 1) avail = 1;
+  const int units = num_work < avail ? num_work : avail;
   cfg.gridDim = dim3(units * CG);
   NBEST_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, tmC, tmC2, g));
   NBEST_CHECK_LAUNCH(ctx);
@@ -534,9 +536,10 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
                   "dropout counter row * N + col would wrap 32 bits (M * N >= 2^32)");
 
   // CTA pairs (256 x BN tiles, tcgen05.mma.cta_group::2) unless NBEST_GEMM_CTA_GROUP=1 asks for the single-CTA kernel.
-  int CG = 2;
-  if (const char* cg = getenv("NBEST_GEMM_CTA_GROUP")) CG = atoi(cg) == 1 ? 1 : 2;
-  const int units = ctx->num_sms / CG;   // persistent work units: CTAs or CTA pairs
+  const int CG = ctx->knobs.gemm_cta_group;
+  // persistent work units: CTAs or CTA pairs. reserve_sms leaves SMs to a collective running next to the GEMM
+  // (nbest_ctx_set_sm_reserve): statically scheduled pairs would otherwise queue behind the SMs it occupies.
+  const int units = (ctx->num_sms - ctx->reserve_sms) / CG;
   const int tile_m = BM * CG;
   // BN = 256 halves the smem operand traffic per MMA. Pairs: always preferred (out-proj T x 768 x 768: 21 us vs 32 us
   // with BN = 128). Single-CTA kernel: short-K problems with few tiles prefer BN = 128 (more, shorter tiles).
@@ -544,10 +547,8 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
   if (CG == 1 && BN == 256 && epilogue != NBEST_EPI_ACCUM_F32 && K <= 1024 &&
       (int64_t)((M + tile_m - 1) / tile_m) * (N / 256) < 4LL * units)
     BN = 128;
-  if (const char* force = getenv("NBEST_GEMM_BN")) {
-    const int f = atoi(force);
-    if ((f == 128 || f == 256) && N % f == 0) BN = f;
-  }
+  if ((ctx->knobs.gemm_force_bn == 128 || ctx->knobs.gemm_force_bn == 256) && N % ctx->knobs.gemm_force_bn == 0)
+    BN = ctx->knobs.gemm_force_bn;
   GemmArgs g;
   g.M = M;
   g.N = N;
@@ -564,22 +565,16 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
     int max_by_k = g.num_kb / 8 > 0 ? g.num_kb / 8 : 1;
     if (want > max_by_k) want = max_by_k;
     if (want < 1) want = 1;
-    if (const char* sp = getenv("NBEST_WGRAD_SPLITS")) {
-      const int v = atoi(sp);
-      if (v >= 1) want = v < max_by_k ? v : max_by_k;
-    }
+    if (ctx->knobs.wgrad_splits >= 1) want = ctx->knobs.wgrad_splits < max_by_k ? ctx->knobs.wgrad_splits : max_by_k;
     g.num_splits = want;
   }
-  g.debug = getenv("NBEST_GEMM_DEBUG") ? atoi(getenv("NBEST_GEMM_DEBUG")) : 0;
+  g.debug = ctx->knobs.gemm_debug;
   const bool two = epilogue == NBEST_EPI_BIAS_GELU;
   g.stages = (CG == 2) ? ((BN == 256) ? (two ? Cfg<256, 2, true>::kStages : Cfg<256, 2>::kStages)
                                       : (two ? Cfg<128, 2, true>::kStages : Cfg<128, 2>::kStages))
                        : ((BN == 256) ? (two ? Cfg<256, 1, true>::kStages : Cfg<256, 1>::kStages)
                                       : (two ? Cfg<128, 1, true>::kStages : Cfg<128, 1>::kStages));
-  if (const char* st = getenv("NBEST_GEMM_STAGES")) {
-    const int v = atoi(st);
-    if (v >= 1 && v < g.stages) g.stages = v;
-  }
+  if (ctx->knobs.gemm_stages >= 1 && ctx->knobs.gemm_stages < g.stages) g.stages = ctx->knobs.gemm_stages;
   g.kb_per_split = (g.num_kb + g.num_splits - 1) / g.num_splits;
   g.num_splits = (g.num_kb + g.kb_per_split - 1) / g.kb_per_split;  // no empty split
   g.C = C;

@@ -58,7 +58,7 @@ def build_adam_tables(spec, device, chunk=16384):
     raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
     return dict(tensors=torch.from_numpy(raw).to(device), n_tensors=n,
                 chunks=torch.tensor(chunks, dtype=torch.int32, device=device).contiguous(), n_chunks=len(chunks),
-                norms=torch.zeros(n, dtype=torch.float32, device=device))
+                norms=torch.zeros(n + len(chunks), dtype=torch.float32, device=device))
 
 
 class FlatBuffers:
