@@ -10,7 +10,7 @@
  * Conventions
  *   - plain C: pointers and sizes only, no torch / C++ types.
  *   - every data pointer is a DEVICE pointer owned by the caller; the library never allocates or frees device
- *     memory. `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it, no internal sync.
+ *     memory (one exception: a 512-byte scheduler buffer owned by the context, see nbest_ctx_set_gemm_dynamic). `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it, no internal sync.
  *   - "bf16" buffers are raw uint16 bfloat16, row-major; "f32" are float.
  *   - return value: NBEST_OK (0) or a negative nbest_status; nbest_last_error(ctx) gives the message.
  *   - one nbest_ctx per process / GPU rank; calls on one ctx must come from one thread at a time.
@@ -47,6 +47,12 @@ uint64_t nbest_launch_count(nbest_ctx* ctx);
  * all-reduce is in flight so that NCCL's CTAs and the statically scheduled CTA pairs do not wait for each other
  * (replaces nothing in the reference: it has no multi-GPU path, utils/gpu_selection.py:27-66 picks ONE device). */
 int nbest_ctx_set_sm_reserve(nbest_ctx* ctx, int n_sms);
+/* on != 0 (the data-parallel trainer's setting for world size > 1; NBEST_GEMM_DYNAMIC=0/1 forces it): the persistent
+ * GEMM CTAs draw their tiles from a global counter instead of a static round-robin share, so a CTA pair whose SMs are
+ * held by a concurrent collective takes fewer tiles rather than delaying its share (measured on B200: +1.7 % step time
+ * on one GPU, where nothing competes for SMs — hence off there — and dgrad GEMMs 6 % faster under NCCL overlap). Needs the context's 512-byte device scheduler buffer — the only device memory the
+ * library allocates itself (nbest_ctx_create / nbest_ctx_destroy). */
+int nbest_ctx_set_gemm_dynamic(nbest_ctx* ctx, int on);
 /* TMA descriptor cache hits so far (host-overhead diagnostics). */
 uint64_t nbest_tmap_cache_hits(nbest_ctx* ctx);
 

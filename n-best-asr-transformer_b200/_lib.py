@@ -34,6 +34,7 @@ _SIGNATURES = {
     "nbest_launch_count": (_u64, [_vp]),
     "nbest_ctx_set_sm_reserve": (C.c_int, [_vp, C.c_int]),
     "nbest_tmap_cache_hits": (_u64, [_vp]),
+    "nbest_ctx_set_gemm_dynamic": (C.c_int, [_vp, C.c_int]),
     "nbest_pack_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nbest_pack_hyp_ids": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "nbest_embed_ln_fwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _f32, C.c_int, _vp, _vp, _vp,
@@ -135,6 +136,9 @@ class Context:
 
     def set_sm_reserve(self, n_sms):
         self.check(self._l.nbest_ctx_set_sm_reserve(self.handle, int(n_sms)))
+
+    def set_gemm_dynamic(self, on):
+        self.check(self._l.nbest_ctx_set_gemm_dynamic(self.handle, int(bool(on))))
 
     def tmap_cache_hits(self):
         return int(self._l.nbest_tmap_cache_hits(self.handle))

@@ -32,6 +32,7 @@ struct nbest_tmap_entry {
   CUtensorMap map;
 };
 constexpr int kTmapCacheSize = 1024;
+constexpr int kSchedRing = 64;        // launches in flight never share a scheduler slot
 
 struct nbest_ctx {
   int device;
@@ -41,6 +42,9 @@ struct nbest_ctx {
   uint64_t launches;                   // kernels launched through this context (bench.py reports it)
   nbest_knobs knobs;
   int reserve_sms;                     // SMs the persistent GEMMs leave free (nbest_ctx_set_sm_reserve)
+  int gemm_dynamic;                    // GEMM work items drawn from a global counter (nbest_ctx_set_gemm_dynamic)
+  uint32_t* sched_buf;                 // device: kSchedRing x {next item, finished units}; the ONE allocation the library owns
+  uint32_t sched_seq;
   uint64_t tmap_hits, tmap_misses;
   nbest_tmap_entry* tmap_cache;
   char err[512];

@@ -69,14 +69,31 @@ extern "C" int nbest_ctx_create(nbest_ctx** out, int device) {
     free(ctx);
     return NBEST_EINVAL;
   }
+  ctx->gemm_dynamic = env_int("NBEST_GEMM_DYNAMIC", 0) != 0;
+  if (cudaMalloc(&ctx->sched_buf, kSchedRing * 2 * sizeof(uint32_t)) != cudaSuccess ||
+      cudaMemset(ctx->sched_buf, 0, kSchedRing * 2 * sizeof(uint32_t)) != cudaSuccess) {
+    snprintf(g_create_err, sizeof(g_create_err), "cannot allocate the %zu-byte GEMM scheduler buffer", kSchedRing * 2 * sizeof(uint32_t));
+    free(ctx->tmap_cache);
+    free(ctx);
+    return NBEST_ECUDA;
+  }
   ctx->err[0] = 0;
   *out = ctx;
   return NBEST_OK;
 }
 
 extern "C" void nbest_ctx_destroy(nbest_ctx* ctx) {
-  if (ctx) free(ctx->tmap_cache);
+  if (ctx) {
+    free(ctx->tmap_cache);
+    cudaFree(ctx->sched_buf);
+  }
   free(ctx);
+}
+
+extern "C" int nbest_ctx_set_gemm_dynamic(nbest_ctx* ctx, int on) {
+  if (!ctx) return NBEST_EINVAL;
+  ctx->gemm_dynamic = on != 0;
+  return NBEST_OK;
 }
 
 extern "C" int nbest_ctx_set_sm_reserve(nbest_ctx* ctx, int n_sms) {

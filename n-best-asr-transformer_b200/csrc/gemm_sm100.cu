@@ -54,7 +54,10 @@ struct GemmArgs {
   uint32_t drop_thresh;
   float drop_scale;
   uint32_t seed;
+  uint32_t* sched;   // {next work item, finished units} of this launch (context-owned, self-resetting), or NULL = static
 };
+
+constexpr int kSchedSlots = 4;   // depth of the work-item ring between the fetching producer and the other warp roles
 
 template <int BN, int CG, bool kTwoOutputs = false>
 struct Cfg {
@@ -91,7 +94,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* sched_full = tempty_bar + 2;
+  uint64_t* sched_empty = sched_full + kSchedSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_empty + kSchedSlots);
+  volatile int32_t* sched_item = reinterpret_cast<volatile int32_t*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -112,6 +118,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], kEpiWarps * CG);   // pair mode: the leader's collects both CTAs' epilogue warps
     }
+    for (int a = 0; a < kSchedSlots; ++a) {
+      mbar_init(&sched_full[a], 1);
+      // a slot is free again once every reader has copied the item: leader = MMA warp + epilogue warps, peer = producer +
+      // epilogue warps; all of them arrive on the LEADER's barrier (the leader's producer is the only writer)
+      mbar_init(&sched_empty[a], (kEpiWarps + 1) * CG);
+    }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
@@ -129,10 +141,55 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // ---- work distribution. Static: unit u takes items u, u + num_units, ... Dynamic (g.sched != NULL): the leader's
+  // producer thread draws items from a global counter and publishes them through a small shared-memory ring to the other
+  // warp roles of the CTA (and of the peer CTA of a pair). A CTA pair that starts late — because a collective holds its
+  // SMs — then simply takes fewer items instead of delaying a statically assigned share of the tiles.
+  const bool dyn = g.sched != nullptr;
+  auto next_item = [&](int i) -> int {     // consumer side: i = running item count of this warp role
+    if (!dyn) {
+      const int w = unit + i * num_units;
+      return w < num_work ? w : -1;
+    }
+    const int slot = i % kSchedSlots;
+    if constexpr (CG == 2) mbar_wait_acquire_cluster(&sched_full[slot], (uint32_t)(i / kSchedSlots) & 1u);
+    else mbar_wait(&sched_full[slot], (uint32_t)(i / kSchedSlots) & 1u);
+    const int w = sched_item[slot];
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&sched_empty[slot]), 0));
+      else mbar_arrive(&sched_empty[slot]);
+    }
+    return w;
+  };
+
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer
     uint32_t stage = 0, phase = 0;
-    for (int w = unit; w < num_work; w += num_units) {
+    int fetched = 0;
+    if (dyn && rank == 0 && lane == 0) fetched = (int)atomicAdd(g.sched, 1u);
+    for (int i = 0;; ++i) {
+      int w;
+      if (dyn && rank == 0) {
+        // leader producer: publish item i (or the end marker) to both CTAs, then draw item i+1 — the atomic's round
+        // trip hides under this item's TMA issue
+        const int slot = i % kSchedSlots;
+        mbar_wait(&sched_empty[slot], ((uint32_t)(i / kSchedSlots) & 1u) ^ 1u);
+        w = __shfl_sync(0xffffffffu, fetched, 0);
+        if (w >= num_work) w = -1;
+        if (lane == 0) {
+          sched_item[slot] = w;
+          mbar_arrive(&sched_full[slot]);
+          if constexpr (CG == 2) {
+            st_shared_cluster_u32(mapa_shared(smem_u32(const_cast<int32_t*>(&sched_item[slot])), 1), (uint32_t)w);
+            mbar_arrive_release_cluster(mapa_shared(smem_u32(&sched_full[slot]), 1));
+          }
+          if (w >= 0) fetched = (int)atomicAdd(g.sched, 1u);
+        }
+      } else {
+        w = next_item(i);
+      }
+      if (w < 0) break;
       const int num_tiles = g.num_m_tiles * g.num_n_tiles;   // tile fastest: concurrent CTAs share one T-range (L2 reuse)
       const int split = w / num_tiles;
       const int tile = w % num_tiles;
@@ -179,7 +236,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr uint32_t a_kstep = A_MN ? 2048 : 32, b_kstep = B_MN ? 2048 : 32;  // bytes per UMMA_K = 16
     uint32_t stage = 0, phase = 0, it = 0;
     if (rank == 0) {
-    for (int w = unit; w < num_work; w += num_units, ++it) {
+    for (;; ++it) {
+      const int w = next_item((int)it);
+      if (w < 0) break;
       const int split = w / (g.num_m_tiles * g.num_n_tiles);
       const int kb0 = split * g.kb_per_split;
       const int kb1 = min(kb0 + g.kb_per_split, g.num_kb);
@@ -231,7 +290,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t it = 0;
     const uint32_t tempty_remote[2] = {(CG == 2) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u,
                                        (CG == 2) ? mapa_shared(smem_u32(&tempty_bar[1]), 0) : 0u};
-    for (int w = unit; w < num_work; w += num_units, ++it) {
+    for (;; ++it) {
+      const int w = next_item((int)it);
+      if (w < 0) break;
       const int tile = w % (g.num_m_tiles * g.num_n_tiles);
       const int m0 = (tile / g.num_n_tiles) * (BM * CG) + (int)rank * BM;   // this CTA's 128 accumulator rows
       const int n0 = (tile % g.num_n_tiles) * BN;
@@ -427,6 +488,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) bulk_wait_all();   // every bulk store of this warp is globally complete before the CTA exits
   }
 
+  if (dyn && warp == kProducerWarp && rank == 0 && lane == 0) {
+    // the last unit to finish re-arms the counters for the launch that will use this scheduler slot next
+    __threadfence();
+    if (atomicAdd(g.sched + 1, 1u) == (uint32_t)num_units - 1u) {
+      g.sched[0] = 0u;
+      g.sched[1] = 0u;
+      __threadfence();
+    }
+  }
   tc_fence_before();
   __syncwarp();
   // pair mode: neither CTA may exit (or free TMEM) while the peer can still read its smem / signal its barriers
@@ -584,6 +654,7 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
   g.ldaux = ldaux;
   g.out2 = reinterpret_cast<__nv_bfloat16*>(out2_bf16);
   g.seed = seed;
+  g.sched = ctx->gemm_dynamic ? ctx->sched_buf + 2 * (ctx->sched_seq++ % kSchedRing) : nullptr;
   if (p_drop > 0.f) {
     const double t = (double)p_drop * 65536.0 + 0.5;   // 16-bit threshold (ptx.cuh dropout_keep)
     g.drop_thresh = t >= 65535.0 ? 65535u : (uint32_t)t;

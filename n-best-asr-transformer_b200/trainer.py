@@ -143,6 +143,11 @@ class DataParallelTrainer:
         # the base seed in the checkpoint stays rank-free
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         model._seed_salt = (rank * 0x9E3779B1) & 0xFFFFFFFF
+        # Under gradient all-reduce overlap NCCL's CTAs hold SMs that statically scheduled persistent GEMM pairs would wait
+        # for: let the GEMMs draw their tiles dynamically (csrc/gemm_sm100.cu). Not on one GPU: there it only costs.
+        if "NBEST_GEMM_DYNAMIC" not in os.environ and model.device.type == "cuda":
+            from . import _lib
+            _lib.context(model.device.index).set_gemm_dynamic(self.world > 1)
         self._bucket_names = {n for n, _, _ in segments}
         if self.overlap_optimizer:
             optimizer.set_buckets(segments)
