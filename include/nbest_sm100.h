@@ -97,6 +97,12 @@ int nbest_embed_ln_bwd(nbest_ctx* ctx, const int32_t* tokens, const uint8_t* seg
  * summed by the GEMM epilogue. */
 int nbest_ln_fwd(nbest_ctx* ctx, const void* x_bf16, const float* gamma, const float* beta, float eps, int T,
                  int hidden, void* y_bf16, float* mean, float* rstd, void* stream);
+/* The same LayerNorm with the row statistics supplied as partial sums: row_partials [T][n_partials] float2 {sum, sum of
+ * squares} over disjoint column groups of the row (what nbest_gemm_bf16 writes to out2 under NBEST_EPI_BIAS_DROP_RES,
+ * n_partials = N / 64 <= 16); NULL = compute them here. One pass over the row instead of two. */
+int nbest_ln_fwd_stats(nbest_ctx* ctx, const void* x_bf16, const float* gamma, const float* beta, float eps, int T,
+                       int hidden, const float* row_partials, int n_partials, void* y_bf16, float* mean, float* rstd,
+                       void* stream);
 /* dx = LN'(dy); dgamma/dbeta accumulated (+=). If dx_masked != NULL it receives dx * dropout_mask / (1-p) (the
  * gradient entering the preceding dense layer, whose output was dropped with (p_drop, seed)); dbias (+=, may be
  * NULL) gets the column sum of that tensor = gradient of the preceding dense bias. */
@@ -125,7 +131,9 @@ typedef enum {
   NBEST_EPI_BIAS = 1,        /* C = acc + bias[n]                                                     */
   NBEST_EPI_BIAS_GELU = 2,   /* u = acc + bias; C = gelu_erf(u); out2 = gelu_erf'(u) (if out2 != NULL): the
                               * derivative is saved instead of u, so that the backward epilogue is one multiply */
-  NBEST_EPI_BIAS_DROP_RES = 3, /* C = dropout(acc + bias[n]; p_drop, seed) + aux[m,n]                 */
+  NBEST_EPI_BIAS_DROP_RES = 3, /* C = dropout(acc + bias[n]; p_drop, seed) + aux[m,n]; if out2 != NULL: out2 (fp32
+                              * [M][N/64][2]) = {sum, sum of squares} of C[m, 64u .. 64u+63]: the partial statistics
+                              * of the residual LayerNorm that follows (nbest_ln_fwd_stats)            */
   NBEST_EPI_DGELU = 4,       /* C = acc * aux[m,n], aux = gelu_erf'(u) saved by NBEST_EPI_BIAS_GELU; if out2 != NULL:
                               * out2 (fp32 [N]) += sum_m C[m,n]
                               * (the bias gradient of the layer that produced aux, fused)              */

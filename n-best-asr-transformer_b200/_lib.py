@@ -42,6 +42,7 @@ _SIGNATURES = {
     "nbest_embed_ln_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _f32, _u32,
                                      _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "nbest_ln_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _f32, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "nbest_ln_fwd_stats": (C.c_int, [_vp, _vp, _vp, _vp, _f32, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     "nbest_ln_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _f32, _u32, _vp, _vp, _vp, _vp]),
     "nbest_colsum_bf16": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "nbest_cast_f32_bf16": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),

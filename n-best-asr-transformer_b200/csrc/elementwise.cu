@@ -265,6 +265,64 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ xin, const float* __restrict__ g
   }
 }
 
+// Residual LayerNorm forward with the row statistics supplied by the producing GEMM (NBEST_EPI_BIAS_DROP_RES writes per-row
+// partial {sum, sum of squares} over its 64-column units: row_part [T][n_part] float2). With mean / rstd known before the
+// row arrives there is no reduction over the row data any more: every 16-byte chunk is normalised and stored as soon as
+// its own load returns — the kernel streams like a copy instead of load -> two warp reductions -> store.
+template <int kRows>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+ln_fwd_stats_kernel(const __nv_bfloat16* __restrict__ xin, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float eps, int T, const float2* __restrict__ row_part, int n_part, __nv_bfloat16* __restrict__ y,
+                    float* __restrict__ mean, float* __restrict__ rstd) {
+  const int lane = threadIdx.x & 31;
+  const int t0 = (blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * kRows;
+  if (t0 >= T) return;
+  uint4 raw[kRows][CPL];
+  float2 part[kRows];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    const int t = min(t0 + r, T - 1);
+    part[r] = lane < n_part ? __ldg(row_part + (int64_t)t * n_part + lane) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) raw[r][i] = __ldg(reinterpret_cast<const uint4*>(xin + (int64_t)t * H) + lane + 32 * i);
+  }
+  float rs[kRows], nm[kRows];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    float s1 = part[r].x, s2 = part[r].y;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {         // n_part <= 16 partials sit in lanes 0..15
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 = __shfl_sync(0xffffffffu, s1, 0);
+    s2 = __shfl_sync(0xffffffffu, s2, 0);
+    const float mu = s1 * (1.0f / H);
+    rs[r] = rsqrtf(fmaxf(s2 * (1.0f / H) - mu * mu, 0.f) + eps);
+    nm[r] = -mu * rs[r];
+    if (lane == 0 && t0 + r < T) {
+      if (mean) mean[t0 + r] = mu;
+      if (rstd) rstd[t0 + r] = rs[r];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = 8 * (lane + 32 * i);
+    float g[8], b[8];
+    load8f(gamma + c, g);
+    load8f(beta + c, b);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      if (t0 + r >= T) break;
+      float x[8], o[8];
+      unpack8(raw[r][i], x);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(fmaf(x[k], rs[r], nm[r]), g[k], b[k]);
+      *(reinterpret_cast<uint4*>(y + (int64_t)(t0 + r) * H) + lane + 32 * i) = pack8(o);
+    }
+  }
+}
+
 // Block-level reduction of per-warp column partials (VPL float4 per lane) followed by one atomic per column per block.
 __device__ __forceinline__ void block_reduce_cols_atomic(float4 (&acc)[VPL], float* __restrict__ out, float* sh /*[warps][H]*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -617,12 +675,17 @@ extern "C" int nbest_embed_ln_bwd(nbest_ctx* ctx, const int32_t* tokens, const u
   return NBEST_OK;
 }
 
-extern "C" int nbest_ln_fwd(nbest_ctx* ctx, const void* x_bf16, const float* gamma, const float* beta, float eps, int T,
-                            int hidden, void* y_bf16, float* mean, float* rstd, void* stream) {
+extern "C" int nbest_ln_fwd_stats(nbest_ctx* ctx, const void* x_bf16, const float* gamma, const float* beta, float eps,
+                                  int T, int hidden, const float* row_partials, int n_partials, void* y_bf16, float* mean,
+                                  float* rstd, void* stream) {
   if (!ctx) return NBEST_EINVAL;
   NBEST_CHECK_ARG(ctx, hidden == H, "hidden must be 768");
   NBEST_CHECK_ARG(ctx, x_bf16 && gamma && beta && y_bf16, "null pointer");
+  NBEST_CHECK_ARG(ctx, row_partials == nullptr || (n_partials >= 1 && n_partials <= 16), "n_partials must be in [1, 16]");
   if (T <= 0) return NBEST_OK;
+  auto* xi = reinterpret_cast<const __nv_bfloat16*>(x_bf16);
+  auto* yo = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static int rows = 0;
   if (rows == 0) {
     const char* e = getenv("NBEST_LN_FWD_ROWS");
@@ -631,14 +694,25 @@ extern "C" int nbest_ln_fwd(nbest_ctx* ctx, const void* x_bf16, const float* gam
   }
   const int rows_per_block = kWarpsPerBlock * rows;
   const int blocks = (T + rows_per_block - 1) / rows_per_block;
-  auto* xi = reinterpret_cast<const __nv_bfloat16*>(x_bf16);
-  auto* yo = reinterpret_cast<__nv_bfloat16*>(y_bf16);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (rows == 1) ln_fwd_kernel<1><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, yo, mean, rstd);
-  else if (rows == 2) ln_fwd_kernel<2><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, yo, mean, rstd);
-  else ln_fwd_kernel<4><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, yo, mean, rstd);
+  if (row_partials != nullptr) {
+    const auto* rp = reinterpret_cast<const float2*>(row_partials);
+    if (rows == 4) ln_fwd_stats_kernel<4><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
+    else if (rows == 1) ln_fwd_stats_kernel<1><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
+    else ln_fwd_stats_kernel<2><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
+  } else if (rows == 1) {
+    ln_fwd_kernel<1><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, yo, mean, rstd);
+  } else if (rows == 2) {
+    ln_fwd_kernel<2><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, yo, mean, rstd);
+  } else {
+    ln_fwd_kernel<4><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, yo, mean, rstd);
+  }
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
+}
+
+extern "C" int nbest_ln_fwd(nbest_ctx* ctx, const void* x_bf16, const float* gamma, const float* beta, float eps, int T,
+                            int hidden, void* y_bf16, float* mean, float* rstd, void* stream) {
+  return nbest_ln_fwd_stats(ctx, x_bf16, gamma, beta, eps, T, hidden, nullptr, 0, y_bf16, mean, rstd, stream);
 }
 
 extern "C" int nbest_ln_bwd(nbest_ctx* ctx, const void* dy_bf16, const void* x_bf16, const float* mean, const float* rstd,

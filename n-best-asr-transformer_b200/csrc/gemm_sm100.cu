@@ -353,6 +353,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (lane == 0) bulk_wait_read();   // the previous store from this buffer has finished reading it
             __syncwarp();
             float dsum = 0.f;                  // EPI_DELTA: dot(acc, aux) over this 64-column unit (= one attention head)
+            float rsum = 0.f, rsq = 0.f;       // EPI_BIAS_DROP_RES: row sum / sum of squares of this unit (LayerNorm statistics)
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
               const int c = 2 * u + cc;
@@ -423,6 +424,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   v[2 * j] += bf16lo(auxrow[j]);
                   v[2 * j + 1] += bf16hi(auxrow[j]);
                 }
+                if (g.out2 != nullptr) {       // partial LayerNorm statistics of the row the next kernel normalises
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) {
+                    rsum += v[j];
+                    rsq = fmaf(v[j], v[j], rsq);
+                  }
+                }
               } else if constexpr (EPI == NBEST_EPI_DGELU) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {   // aux = gelu'(u), saved by the forward's NBEST_EPI_BIAS_GELU epilogue
@@ -450,6 +458,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             if constexpr (EPI == NBEST_EPI_DELTA) {
               if (row < g.M) reinterpret_cast<float*>(g.out2)[(int64_t)((n0 >> 6) + u) * g.M + row] = dsum;
+            }
+            if constexpr (EPI == NBEST_EPI_BIAS_DROP_RES) {
+              if (g.out2 != nullptr && row < g.M)
+                reinterpret_cast<float2*>(g.out2)[(int64_t)row * (g.N >> 6) + (n0 >> 6) + u] = make_float2(rsum, rsq);
             }
             fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
             __syncwarp();

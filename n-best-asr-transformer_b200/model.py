@@ -405,17 +405,19 @@ class TOD_ASR_Transformer_STC(nn.Module):
                     ops.attn_fwd(qkv, pk.cu_seqlens, kv, pk.B, pk.max_len, s.heads, T, ctx, L.lse, p_a, self._seed(l, 1),
                                  sum_l2=pk.sum_l2)
                 resid = x
-            ops.gemm(ctx, w["h_wo"], epilogue=ops.EPI_BIAS_DROP_RES, bias=w["p_bo"], aux=resid, out=pre1, p_drop=p_h,
+            # the GEMM epilogue also emits the rows' partial {sum, sum of squares}: the LayerNorm behind it is single-pass
+            part = self._row_partials(n)
+            ops.gemm(ctx, w["h_wo"], epilogue=ops.EPI_BIAS_DROP_RES, bias=w["p_bo"], aux=resid, out=pre1, out2=part, p_drop=p_h,
                      seed=self._seed(l, 2))
             L.mean1, L.rstd1 = f32(n), f32(n)
-            ops.ln_fwd(pre1, w["p_g1"], w["p_b1"], s.ln_eps, x1, L.mean1, L.rstd1)
+            ops.ln_fwd(pre1, w["p_g1"], w["p_b1"], s.ln_eps, x1, L.mean1, L.rstd1, row_partials=part)
             # gact = gelu(x1 W1 + b); u = gelu'(x1 W1 + b) — the derivative is saved, so the backward epilogue only multiplies
             ops.gemm(x1, w["h_w1"], epilogue=ops.EPI_BIAS_GELU, bias=w["p_bi"], out=gact, out2=u)
-            ops.gemm(gact, w["h_w2"], epilogue=ops.EPI_BIAS_DROP_RES, bias=w["p_b2o"], aux=x1, out=pre2, p_drop=p_h,
+            ops.gemm(gact, w["h_w2"], epilogue=ops.EPI_BIAS_DROP_RES, bias=w["p_b2o"], aux=x1, out=pre2, out2=part, p_drop=p_h,
                      seed=self._seed(l, 3))
             L.mean2, L.rstd2 = f32(n), f32(n)
             x_out = bf(n, H) if (save or last_cls) else self._pingpong(x, T)
-            ops.ln_fwd(pre2, w["p_g2"], w["p_b2"], s.ln_eps, x_out, L.mean2, L.rstd2)
+            ops.ln_fwd(pre2, w["p_g2"], w["p_b2"], s.ln_eps, x_out, L.mean2, L.rstd2, row_partials=part)
             L.qkv, L.ctx, L.pre1, L.x1, L.u, L.g, L.pre2 = qkv, ctx, pre1, x1, u, gact, pre2
             if save:
                 sv.layers.append(L)
@@ -432,6 +434,17 @@ class TOD_ASR_Transformer_STC(nn.Module):
                 self._arange_i32 = ar
             return ar[row0:row0 + B + 1]
         return sv.pk.cu_seqlens[row0:row0 + B + 1]
+
+    def _row_partials(self, n):
+        """fp32 [n, 12, 2] workspace for the LayerNorm partial statistics a DROP_RES GEMM epilogue writes (re-used: each
+        GEMM -> LayerNorm pair is adjacent in stream order)."""
+        if not getattr(self, "ln_fused_stats", True):
+            return None
+        ws = getattr(self, "_part_ws", None)
+        if ws is None or ws.shape[0] < n:
+            ws = torch.empty((max(n, 1024), H // 64, 2), device=self.device, dtype=torch.float32)
+            self._part_ws = ws
+        return ws[:n]
 
     def _pingpong(self, x, T):
         """Inference: two alternating hidden-state buffers instead of one per layer."""

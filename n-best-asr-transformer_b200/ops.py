@@ -243,11 +243,18 @@ def embed_ln_bwd(pk, word, posemb, type_emb, gamma, mean, rstd, dy, dword, dpos,
                                                 _p(dbeta), int(word_pad_row), int(pos_pad_row), _stream()))
 
 
-def ln_fwd(x, gamma, beta, eps, y, mean=None, rstd=None, T=None):
+def ln_fwd(x, gamma, beta, eps, y, mean=None, rstd=None, T=None, row_partials=None):
+    """row_partials: fp32 [T, n, 2] per-row partial {sum, sum of squares} written by the producing GEMM (EPI_BIAS_DROP_RES
+    with out2=...): the LayerNorm then needs one pass over the row."""
     ctx = _ctx(x)
+    n_part = 0
+    if row_partials is not None:
+        if row_partials.dtype != torch.float32 or not row_partials.is_contiguous() or row_partials.dim() != 3:
+            raise ValueError("row_partials must be a contiguous fp32 [T, n, 2] tensor")
+        n_part = row_partials.shape[1]
     with _Timed('ln_fwd', 0.0, (x.shape[0] if T is None else T) * (2 * 768 * 2.0)):
-        ctx.check(_lib.lib().nbest_ln_fwd(ctx.handle, _p(x), _p(gamma), _p(beta), float(eps), x.shape[0] if T is None else T,
-                                          x.shape[1], _p(y), _p(mean), _p(rstd), _stream()))
+        ctx.check(_lib.lib().nbest_ln_fwd_stats(ctx.handle, _p(x), _p(gamma), _p(beta), float(eps), x.shape[0] if T is None else T,
+                                                x.shape[1], _p(row_partials), n_part, _p(y), _p(mean), _p(rstd), _stream()))
 
 
 def ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dx_masked=None, dbias=None, p_drop=0.0, seed=0, T=None):

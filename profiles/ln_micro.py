@@ -17,6 +17,10 @@ for T in (17920, 12160):
     y = torch.empty_like(xs[0]); mean = torch.empty(T, device="cuda"); rstd = torch.empty(T, device="cuda")
     us = timeit(lambda i: ops.ln_fwd(xs[i % 6], g, b, 1e-12, y, mean, rstd))
     print("T=%d ln_fwd  %6.1f us  %5.0f GB/s (4 B/elem)" % (T, us, T * H * 4 / us / 1e3))
+    part = torch.zeros(T, H // 64, 2, device="cuda")
+    part[:, :, 0] = xs[0].float().view(T, H // 64, 64).sum(-1); part[:, :, 1] = (xs[0].float() ** 2).view(T, H // 64, 64).sum(-1)
+    us = timeit(lambda i: ops.ln_fwd(xs[i % 6], g, b, 1e-12, y, mean, rstd, row_partials=part))
+    print("T=%d ln_fwd with GEMM-epilogue row statistics  %6.1f us  %5.0f GB/s" % (T, us, T * H * 4 / us / 1e3))
     dx, dxm = torch.empty_like(y), torch.empty_like(y)
     dg, db, dbi = (torch.zeros(H, device="cuda") for _ in range(3))
     us = timeit(lambda i: ops.ln_bwd(dys[i % 6], xs[i % 6], mean, rstd, g, dx, dg, db, dx_masked=dxm, dbias=dbi, p_drop=0.1, seed=i))

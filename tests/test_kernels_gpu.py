@@ -696,3 +696,35 @@ def test_attention_tile_kernels_dropout_masks_are_the_shared_index_map():
     ops.attn_tiles_bwd(qkv, plan, 0, key_valid, heads, T, T, dout, lse_b, delta, T, dq_a, p_drop=pa, seed=seed)
     ops.attn_bwd(qkv, cu_d, key_valid, B, max(lens), heads, T, None, dout, lse_b, dq_b, delta, p_drop=pa, seed=seed)
     assert _rel(dq_a, dq_b) < 1e-2 and _cos(dq_a, dq_b) > 0.9999
+
+
+def test_ln_fwd_with_row_statistics_from_the_gemm_epilogue():
+    """NBEST_EPI_BIAS_DROP_RES with out2 = row-partial buffer: {sum, sum of squares} per 64-column unit of the result; the
+    single-pass LayerNorm fed with them equals the two-pass one (statistics from the rounded row) and the fp32 reference."""
+    from nbest_b200 import ops
+    T, K = 1000, 768
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(T, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(H, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(H, device="cuda", generator=g)
+    res = (torch.randn(T, H, device="cuda", generator=g) * 2 + 0.7).to(torch.bfloat16)     # non-zero mean rows
+    part = torch.zeros(T, H // 64, 2, device="cuda")
+    pre = ops.gemm(a, w, epilogue=ops.EPI_BIAS_DROP_RES, bias=bias, aux=res, out2=part, p_drop=0.1, seed=77)
+    pre_plain = ops.gemm(a, w, epilogue=ops.EPI_BIAS_DROP_RES, bias=bias, aux=res, p_drop=0.1, seed=77)
+    assert torch.equal(pre, pre_plain)                                   # emitting the statistics does not change the result
+    units = pre.float().view(T, H // 64, 64)
+    assert _rel(part[:, :, 0], units.sum(-1)) < 2e-3 and _rel(part[:, :, 1], (units ** 2).sum(-1)) < 4e-3
+    gamma, beta = torch.randn(H, device="cuda", generator=g), torch.randn(H, device="cuda", generator=g)
+    y1, y2 = torch.empty_like(pre), torch.empty_like(pre)
+    m1, r1, m2, r2 = (torch.empty(T, device="cuda") for _ in range(4))
+    ops.ln_fwd(pre, gamma, beta, 1e-12, y1, m1, r1, row_partials=part)
+    ops.ln_fwd(pre, gamma, beta, 1e-12, y2, m2, r2)
+    ref = torch.nn.functional.layer_norm(pre.float(), (H,), gamma, beta, 1e-12)
+    assert _rel(m1, m2) < 2e-3 and _rel(r1, r2) < 2e-3
+    assert _rel(y1, ref) < 1e-2 and _rel(y2, ref) < 1e-2 and _rel(y1, y2) < 1e-2
+    # ragged row count (not a multiple of the 128-row tile) and rows the persistent grid wraps around
+    T2 = 40011
+    x = (torch.randn(T2, H, device="cuda", generator=g) * 1.5).to(torch.bfloat16)
+    y = torch.empty_like(x)
+    ops.ln_fwd(x, gamma, beta, 1e-5, y)
+    assert _rel(y, torch.nn.functional.layer_norm(x.float(), (H,), gamma, beta, 1e-5)) < 1e-2
