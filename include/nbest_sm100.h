@@ -76,6 +76,21 @@ int nbest_pack_batch(nbest_ctx* ctx, const int64_t* ids, const int64_t* seg_ids,
  * 255). tokens / cu_seqlens are nbest_pack_batch outputs. */
 int nbest_pack_hyp_ids(nbest_ctx* ctx, const int32_t* tokens, const int32_t* cu_seqlens, int B, int sep_id,
                        uint8_t* hyp_id, void* stream);
+/* Both encoder streams of one step (ASR n-best sequences first, then the transcripts: n_best_asr_bert.py:249-250 builds
+ * the two padded batches, models/model.py:43-58 runs the encoder on each) packed into ONE batch in place: lens /
+ * cu_seqlens over B_a + B_t sequences, token arrays with capacity B_a*S_a + B_t*S_t. Same per-token contract as
+ * nbest_pack_batch; seg_a / seg_t may be NULL. */
+int nbest_pack_batch_dual(nbest_ctx* ctx, const int64_t* ids_a, const int64_t* seg_a, int B_a, int S_a, const int64_t* ids_t,
+                          const int64_t* seg_t, int B_t, int S_t, int pos_mode, int32_t* lens, int32_t* cu_seqlens,
+                          int32_t* tokens, uint8_t* seg, int32_t* pos, int32_t* seq_of, uint8_t* key_valid, void* stream);
+/* Row gather / scatter of [*, 768] bf16 activations by packed row index — the [CLS] slice `sequence_output[:, 0, :]` of
+ * models/model.py:46-47,57-58 and its autograd scatter. gather: dst[i] = src[row_idx[i]] (fp32 dst if dst_is_f32);
+ * scatter: dst [T, 768] = 0 except dst[row_idx[i]] = src[i]. nbest_zero: asynchronous zero-fill (gradient buffers). */
+int nbest_rows_gather(nbest_ctx* ctx, const void* src_bf16, const int32_t* row_idx, int n, int hidden, void* dst,
+                      int dst_is_f32, void* stream);
+int nbest_rows_scatter(nbest_ctx* ctx, const void* src_bf16, const int32_t* row_idx, int n, int T, int hidden,
+                       void* dst_bf16, void* stream);
+int nbest_zero(nbest_ctx* ctx, void* ptr, int64_t nbytes, void* stream);
 
 /* ---- K1: embedding gather + LayerNorm (+dropout) ---------------------------------------------------------- */
 /* BertEmbeddings.forward (transformers/models/bert/modeling_bert.py:102-112), called from models/model.py:43-45.

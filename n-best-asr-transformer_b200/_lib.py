@@ -37,6 +37,11 @@ _SIGNATURES = {
     "nbest_ctx_set_gemm_dynamic": (C.c_int, [_vp, C.c_int]),
     "nbest_pack_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nbest_pack_hyp_ids": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "nbest_pack_batch_dual": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp,
+                                        _vp, _vp, _vp, _vp]),
+    "nbest_rows_gather": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]),
+    "nbest_rows_scatter": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "nbest_zero": (C.c_int, [_vp, _vp, _i64, _vp]),
     "nbest_embed_ln_fwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _f32, C.c_int, _vp, _vp, _vp,
                                      _f32, _u32, _vp]),
     "nbest_embed_ln_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _f32, _u32,

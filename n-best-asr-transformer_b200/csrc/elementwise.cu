@@ -68,10 +68,11 @@ __global__ void pack_scan_kernel(const int32_t* __restrict__ lens, int B, int32_
 __global__ void pack_scatter_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ seg_ids, int B, int S,
                                     int pos_mode, const int32_t* __restrict__ cu, int32_t* __restrict__ tokens,
                                     uint8_t* __restrict__ seg, int32_t* __restrict__ pos, int32_t* __restrict__ seq_of,
-                                    uint8_t* __restrict__ key_valid) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                                    uint8_t* __restrict__ key_valid, int row0) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
   const int lane = threadIdx.x & 31;
+  cu += row0;                               // this stream's sequences sit at [row0, row0 + B) of the merged batch
   const int t0 = cu[row], L = cu[row + 1] - cu[row];
   int carry = 0;
   for (int c = 0; c < L; c += 32) {
@@ -84,7 +85,7 @@ __global__ void pack_scatter_kernel(const int64_t* __restrict__ ids, const int64
       const int t = t0 + j;
       tokens[t] = (int32_t)id;
       seg[t] = seg_ids ? (uint8_t)seg_ids[(int64_t)row * S + j] : (uint8_t)0;
-      seq_of[t] = row;
+      seq_of[t] = row0 + row;
       key_valid[t] = id > 0 ? 1 : 0;
       if (pos_mode == 1) {
         const int incl = carry + __popc(m & (0xffffffffu >> (31 - lane)));
@@ -695,8 +696,96 @@ extern "C" int nbest_pack_batch(nbest_ctx* ctx, const int64_t* ids, const int64_
   NBEST_CHECK_LAUNCH(ctx);
   pack_scan_kernel<<<1, 1024, 0, s>>>(lens, B, cu_seqlens);
   NBEST_CHECK_LAUNCH(ctx);
-  pack_scatter_kernel<<<blocks, 256, 0, s>>>(ids, seg_ids, B, S, pos_mode, cu_seqlens, tokens, seg, pos, seq_of, key_valid);
+  pack_scatter_kernel<<<blocks, 256, 0, s>>>(ids, seg_ids, B, S, pos_mode, cu_seqlens, tokens, seg, pos, seq_of, key_valid, 0);
   NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
+extern "C" int nbest_pack_batch_dual(nbest_ctx* ctx, const int64_t* ids_a, const int64_t* seg_a, int B_a, int S_a,
+                                     const int64_t* ids_t, const int64_t* seg_t, int B_t, int S_t, int pos_mode, int32_t* lens,
+                                     int32_t* cu_seqlens, int32_t* tokens, uint8_t* seg, int32_t* pos, int32_t* seq_of,
+                                     uint8_t* key_valid, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, ids_a && ids_t && lens && cu_seqlens && tokens && seg && pos && seq_of && key_valid, "null pointer");
+  NBEST_CHECK_ARG(ctx, B_a > 0 && S_a > 0 && B_t > 0 && S_t > 0, "empty batch");
+  NBEST_CHECK_ARG(ctx, pos_mode == 0 || pos_mode == 1, "pos_mode must be 0 (bert) or 1 (xlm-roberta)");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  pack_lens_kernel<<<(B_a + 7) / 8, 256, 0, s>>>(ids_a, B_a, S_a, lens);
+  NBEST_CHECK_LAUNCH(ctx);
+  pack_lens_kernel<<<(B_t + 7) / 8, 256, 0, s>>>(ids_t, B_t, S_t, lens + B_a);
+  NBEST_CHECK_LAUNCH(ctx);
+  pack_scan_kernel<<<1, 1024, 0, s>>>(lens, B_a + B_t, cu_seqlens);
+  NBEST_CHECK_LAUNCH(ctx);
+  pack_scatter_kernel<<<(B_a + 7) / 8, 256, 0, s>>>(ids_a, seg_a, B_a, S_a, pos_mode, cu_seqlens, tokens, seg, pos, seq_of, key_valid, 0);
+  NBEST_CHECK_LAUNCH(ctx);
+  pack_scatter_kernel<<<(B_t + 7) / 8, 256, 0, s>>>(ids_t, seg_t, B_t, S_t, pos_mode, cu_seqlens, tokens, seg, pos, seq_of, key_valid, B_a);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
+// dst[i, :] = src[row_idx[i], :] (bf16 -> bf16, or bf16 -> fp32 when dst_f32); one warp per row, 16-byte chunks
+__global__ void rows_gather_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ row_idx, int n,
+                                   void* __restrict__ dst, int dst_f32) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* sp = reinterpret_cast<const uint4*>(src + (int64_t)row_idx[i] * H);
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const uint4 v = __ldg(sp + lane + 32 * c);
+    if (!dst_f32) {
+      *(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dst) + (int64_t)i * H) + lane + 32 * c) = v;
+    } else {
+      float f[8];
+      unpack8(v, f);
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + (int64_t)i * H + 8 * (lane + 32 * c));
+      o[0] = make_float4(f[0], f[1], f[2], f[3]);
+      o[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
+}
+// dst[row_idx[i], :] = src[i, :] (bf16); the caller zero-fills dst
+__global__ void rows_scatter_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ row_idx, int n,
+                                    __nv_bfloat16* __restrict__ dst) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* sp = reinterpret_cast<const uint4*>(src + (int64_t)i * H);
+  uint4* dp = reinterpret_cast<uint4*>(dst + (int64_t)row_idx[i] * H);
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) dp[lane + 32 * c] = __ldg(sp + lane + 32 * c);
+}
+
+extern "C" int nbest_rows_gather(nbest_ctx* ctx, const void* src_bf16, const int32_t* row_idx, int n, int hidden, void* dst,
+                                 int dst_is_f32, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, hidden == H, "hidden must be 768");
+  NBEST_CHECK_ARG(ctx, src_bf16 && row_idx && dst, "null pointer");
+  if (n <= 0) return NBEST_OK;
+  rows_gather_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src_bf16), row_idx, n, dst, dst_is_f32);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
+extern "C" int nbest_rows_scatter(nbest_ctx* ctx, const void* src_bf16, const int32_t* row_idx, int n, int T, int hidden,
+                                  void* dst_bf16, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, hidden == H, "hidden must be 768");
+  NBEST_CHECK_ARG(ctx, src_bf16 && row_idx && dst_bf16 && T >= 0, "null pointer");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  NBEST_CHECK_CUDA(ctx, cudaMemsetAsync(dst_bf16, 0, (size_t)T * H * 2, s));
+  if (n <= 0) return NBEST_OK;
+  rows_scatter_kernel<<<(n + 7) / 8, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src_bf16), row_idx, n,
+                                                  reinterpret_cast<__nv_bfloat16*>(dst_bf16));
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
+extern "C" int nbest_zero(nbest_ctx* ctx, void* ptr, int64_t nbytes, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, ptr && nbytes >= 0, "null pointer");
+  NBEST_CHECK_CUDA(ctx, cudaMemsetAsync(ptr, 0, (size_t)nbytes, reinterpret_cast<cudaStream_t>(stream)));
   return NBEST_OK;
 }
 

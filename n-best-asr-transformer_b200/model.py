@@ -315,7 +315,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
             f.bf16_version = f.params._version
 
     def zero_grad(self, set_to_none=False):
-        self.flat.grads.zero_()
+        ops.zero_(self.flat.grads)
 
     # ------------------------------------------------------------------------------------------------ packing
     def _pack_streams(self, input_ids, seg_ids, trans_input_ids, trans_seg_ids, lens=None, trans_lens=None,
@@ -330,25 +330,18 @@ class TOD_ASR_Transformer_STC(nn.Module):
             for t in (seg_ids, trans_seg_ids):                  # HF would raise IndexError in the token-type embedding
                 if t is not None and int(t.max()) >= self.spec.type_vocab:
                     raise IndexError("token type id %d out of range for type_vocab_size %d" % (int(t.max()), self.spec.type_vocab))
-        pa = ops.pack_batch(input_ids, seg_ids, kind, lens)
+        if trans_input_ids is not None:
+            # one packing pass writes both streams in place (no concatenation kernels)
+            pk = ops.pack_batch_dual(input_ids, seg_ids, lens, trans_input_ids, trans_seg_ids, trans_lens, kind)
+        else:
+            pa = ops.pack_batch(input_ids, seg_ids, kind, lens)
         if trans_input_ids is None:
             pa.B_asr, pa.T_asr, pa.max_len_asr = pa.B, pa.T, pa.max_len
             pa.sum_l2_asr = pa.sum_l2
             if self.attn_tensor_path:
                 pa.plan = ops.attn_plan(pa.cu_seqlens, pa.seq_of, pa.B, pa.T)
             return pa
-        pt = ops.pack_batch(trans_input_ids, trans_seg_ids, kind, trans_lens)
-        pk = ops.Packed()
-        pk.B, pk.S = pa.B + pt.B, max(pa.S, pt.S)
-        pk.T, pk.max_len = pa.T + pt.T, max(pa.max_len, pt.max_len)
-        pk.lens = torch.cat([pa.lens, pt.lens])
-        pk.cu_seqlens = torch.cat([pa.cu_seqlens, pt.cu_seqlens[1:] + pa.T])
-        for f in ("tokens", "seg", "pos", "key_valid"):
-            setattr(pk, f, torch.cat([getattr(pa, f)[:pa.T], getattr(pt, f)[:pt.T]]))
-        pk.seq_of = torch.cat([pa.seq_of[:pa.T], pt.seq_of[:pt.T] + pa.B])
-        pk.B_asr, pk.T_asr, pk.max_len_asr = pa.B, pa.T, pa.max_len
-        pk.sum_l2, pk.sum_l2_asr = pa.sum_l2 + pt.sum_l2, pa.sum_l2
-        pk.plan = ops.attn_plan(pk.cu_seqlens, pk.seq_of, pk.B, pk.T, break_at=pa.B) if self.attn_tensor_path else None
+        pk.plan = ops.attn_plan(pk.cu_seqlens, pk.seq_of, pk.B, pk.T, break_at=pk.B_asr) if self.attn_tensor_path else None
         return pk
 
     def _seed(self, layer, site):
@@ -393,7 +386,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
             if last_cls:
                 L.lse = f32(s.heads, pk.B)
                 ops.attn_cls_fwd(qkv, pk.cu_seqlens, kv, pk.B, pk.max_len, s.heads, T, ctx, L.lse, p_a, self._seed(l, 1))
-                resid = x.index_select(0, pk.cu_seqlens[:pk.B].long())
+                resid = ops.rows_gather(x, pk.cu_seqlens, pk.B, bf(pk.B, H))
             else:
                 L.lse = f32(s.heads, T)
                 if pk.plan is not None:
@@ -502,8 +495,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
             if compact:
                 ops.attn_cls_bwd(L.qkv, cu, kv, B_act, max_len, s.heads, T, L.ctx, dctx, L.lse, pk.B, dqkv, p_a, self._seed(l, 1))
                 # the residual branch reaches the layer input only at the CLS rows
-                dres = torch.zeros((T_act, H), device=dev, dtype=torch.bfloat16)
-                dres.index_copy_(0, cu[:B_act].long(), dpre)
+                dres = ops.rows_scatter(dpre, cu, B_act, T_act, bf(T_act, H))
                 dx = bf(T_act, H)
             else:
                 l2s = pk.sum_l2 if B_act == pk.B else pk.sum_l2_asr
@@ -548,10 +540,8 @@ class TOD_ASR_Transformer_STC(nn.Module):
         return o
 
     def _cls_rows(self, sv, row0, B):
-        if sv.cls_compact:
-            return sv.x_last[row0:row0 + B].float()
-        idx = sv.pk.cu_seqlens[row0:row0 + B].long()
-        return sv.x_last.index_select(0, idx).float()
+        out = torch.empty((B, H), device=self.device, dtype=torch.float32)
+        return ops.rows_gather(sv.x_last, self._cls_cu(sv, row0, B), B, out)
 
     def _backward_from_dlogits(self, sv, ho, dlogits, d_cls_asr, d_cls_trans, head_on_trans=False):
         """dlogits [B,n_cols] (+ optional direct gradients of the two CLS vectors) -> all parameter gradients."""
@@ -643,7 +633,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
         B = pk.B_asr
         ho = self._head_forward(sv, B)
         dev = self.device
-        losses = torch.zeros(4, device=dev, dtype=torch.float32)
+        losses = ops.zero_(torch.empty(4, device=dev, dtype=torch.float32))
         dlogits = torch.empty((B, self.hier.n_cols), device=dev, dtype=torch.float32)
         use_l2 = add_l2_loss and trans_input_ids is not None
         trans_cls = d_asr = d_trans = None

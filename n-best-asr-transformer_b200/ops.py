@@ -214,6 +214,80 @@ def pack_batch(ids, seg_ids=None, kind="bert", lens_host=None):
     return pk
 
 
+def pack_batch_dual(ids_a, seg_a, lens_a, ids_t, seg_t, lens_t, kind="bert"):
+    """Both streams of a step -> ONE Packed batch (ASR sequences first), written in place by nbest_pack_batch_dual."""
+    for t in (ids_a, ids_t):
+        if t.dtype != torch.int64 or t.dim() != 2 or not t.is_cuda:
+            raise ValueError("ids must be int64 [B,S] CUDA tensors")
+    ids_a, ids_t = ids_a.contiguous(), ids_t.contiguous()
+    for sg, ref in ((seg_a, ids_a), (seg_t, ids_t)):
+        if sg is not None and (sg.dtype != torch.int64 or sg.shape != ref.shape or not sg.is_cuda):
+            raise ValueError("seg_ids must be an int64 CUDA tensor shaped like ids")
+    seg_a = seg_a.contiguous() if seg_a is not None else None
+    seg_t = seg_t.contiguous() if seg_t is not None else None
+    (Ba, Sa), (Bt, St) = ids_a.shape, ids_t.shape
+    dev = ids_a.device
+    pk = Packed()
+    pk.B, pk.S = Ba + Bt, max(Sa, St)
+    pk.plan = pk.plan_asr = None
+    cap = Ba * Sa + Bt * St
+    ws = torch.empty(3 * cap + 2 * (Ba + Bt) + 1, dtype=torch.int32, device=dev)      # one allocation for the int32 arrays
+    pk.tokens, pk.pos, pk.seq_of = ws[:cap], ws[cap:2 * cap], ws[2 * cap:3 * cap]
+    pk.lens = ws[3 * cap:3 * cap + Ba + Bt]
+    pk.cu_seqlens = ws[3 * cap + Ba + Bt:]
+    w8 = torch.empty(2 * cap, dtype=torch.uint8, device=dev)
+    pk.seg, pk.key_valid = w8[:cap], w8[cap:]
+    ctx = _ctx(ids_a)
+    with _Timed('pack_batch', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_pack_batch_dual(ctx.handle, _p(ids_a), _p(seg_a), Ba, Sa, _p(ids_t), _p(seg_t), Bt, St,
+                                                   1 if kind == "xlm-roberta" else 0, _p(pk.lens), _p(pk.cu_seqlens),
+                                                   _p(pk.tokens), _p(pk.seg), _p(pk.pos), _p(pk.seq_of), _p(pk.key_valid),
+                                                   _stream()))
+    if lens_a is not None and lens_t is not None and kind != "xlm-roberta":
+        if len(lens_a) != Ba or len(lens_t) != Bt or max(lens_a) > Sa or max(lens_t) > St or min(lens_a) < 0 or min(lens_t) < 0:
+            raise ValueError("input_lens do not describe the id tensors")
+        la, lt = [int(x) for x in lens_a], [int(x) for x in lens_t]
+        if _CHECK_LENS and pk.lens.cpu().tolist() != la + lt:
+            raise ValueError("input_lens disagrees with the lengths derived from ids")
+    else:
+        lc = pk.lens.cpu().tolist()
+        la, lt = lc[:Ba], lc[Ba:]
+    pk.T_asr, pk.max_len_asr, pk.B_asr = sum(la), max(la), Ba
+    pk.T, pk.max_len = pk.T_asr + sum(lt), max(pk.max_len_asr, max(lt))
+    if _PROF is not None or lens_a is None:
+        pk.sum_l2_asr = float(sum(x * x for x in la))
+        pk.sum_l2 = pk.sum_l2_asr + float(sum(x * x for x in lt))
+    else:
+        pk.sum_l2 = pk.sum_l2_asr = 0.0
+    return pk
+
+
+def rows_gather(src, row_idx, n, out):
+    """out[i] = src[row_idx[i]] for [*, 768] bf16 rows; out may be bf16 or fp32 (see nbest_rows_gather)."""
+    ctx = _ctx(src)
+    _check_bf16(src, "src")
+    with _Timed('rows_gather', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_rows_gather(ctx.handle, _p(src), _p(row_idx), int(n), src.shape[1], _p(out),
+                                               int(out.dtype == torch.float32), _stream()))
+    return out
+
+
+def rows_scatter(src, row_idx, n, T, out):
+    """out [T, 768] bf16 = 0 except out[row_idx[i]] = src[i] (see nbest_rows_scatter)."""
+    ctx = _ctx(src)
+    _check_bf16(src, "src")
+    with _Timed('rows_scatter', 0.0, 0.0):
+        ctx.check(_lib.lib().nbest_rows_scatter(ctx.handle, _p(src), _p(row_idx), int(n), int(T), src.shape[1], _p(out), _stream()))
+    return out
+
+
+def zero_(t):
+    """Asynchronous zero-fill of a contiguous tensor on the bound stream (gradient / accumulator buffers)."""
+    ctx = _ctx(t)
+    ctx.check(_lib.lib().nbest_zero(ctx.handle, _p(t), t.numel() * t.element_size(), _stream()))
+    return t
+
+
 def pack_hyp_ids(pk, sep_id, B=None):
     """uint8 [T] hypothesis index of every packed token (see nbest_pack_hyp_ids): 0 = [CLS] + system turn + first [SEP]."""
     B = pk.B if B is None else B

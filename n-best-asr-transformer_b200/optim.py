@@ -196,7 +196,7 @@ class BertAdam(torch.optim.Optimizer):
 
     def zero_grad(self, set_to_none=False):
         """Keeps .grad tensors alive as views of the flat gradient buffer (one memset instead of 221 kernels)."""
-        self.flat.grads.zero_()
+        ops.zero_(self.flat.grads)
 
     def _hyper(self):
         out = []

@@ -728,3 +728,28 @@ def test_ln_fwd_with_row_statistics_from_the_gemm_epilogue():
     y = torch.empty_like(x)
     ops.ln_fwd(x, gamma, beta, 1e-5, y)
     assert _rel(y, torch.nn.functional.layer_norm(x.float(), (H,), gamma, beta, 1e-5)) < 1e-2
+
+
+def test_hypothesis_id_map_bit_exact():
+    """nbest_pack_hyp_ids: hyp_id[t] = number of separator tokens before position t of its sequence (north_star (1):
+    the segment / hypothesis-id map is built on the GPU) — bit-exact against a numpy restatement, BERT and XLM-R ids."""
+    from nbest_b200 import ops
+    rng = np.random.RandomState(4)
+    for kind, sep, pad, first in (("bert", 102, 0, 101), ("xlm-roberta", 2, 1, 0)):
+        B, S = 37, 150
+        lens = rng.randint(1, S + 1, size=B)
+        lens[0], lens[1] = S, 1
+        ids = np.full((B, S), pad, dtype=np.int64)
+        for b in range(B):
+            row = rng.randint(1000, 30000, size=lens[b])
+            row[rng.rand(lens[b]) < 0.15] = sep
+            row[0] = first
+            ids[b, :lens[b]] = row
+        pk = ops.pack_batch(torch.from_numpy(ids).cuda(), None, kind)
+        got = ops.pack_hyp_ids(pk, sep).cpu().numpy()
+        tok, cu = pk.tokens[:pk.T].cpu().numpy(), pk.cu_seqlens.cpu().numpy()
+        exp = np.zeros(pk.T, dtype=np.uint8)
+        for b in range(B):
+            seg = tok[cu[b]:cu[b + 1]] == sep
+            exp[cu[b]:cu[b + 1]] = np.minimum(255, np.concatenate([[0], np.cumsum(seg)[:-1]]))
+        assert np.array_equal(got, exp), kind
