@@ -91,6 +91,16 @@ int nbest_rows_gather(nbest_ctx* ctx, const void* src_bf16, const int32_t* row_i
 int nbest_rows_scatter(nbest_ctx* ctx, const void* src_bf16, const int32_t* row_idx, int n, int T, int hidden,
                        void* dst_bf16, void* stream);
 int nbest_zero(nbest_ctx* ctx, void* ptr, int64_t nbytes, void* stream);
+/* Row-sparse exchange of the word-embedding gradient in the data-parallel trainer (the reference has no multi-GPU path;
+ * its dense embedding gradient comes from autograd, n_best_asr_bert.py:264 — of XLM-R's 250,002 x 768 table at most T
+ * rows are non-zero per step). phase 0: flags[n_rows] = 0, then flags[tokens[t]] = 1 for t < T; (the caller MAX-reduces
+ * flags over the ranks;) phase 1: rows[0..count) = ascending row indices with a set flag, except skip_row (padding_idx:
+ * its gradient row is zero by construction). nbest_rows_move_f32: gather (dst[i] = src[rows[i]]) or scatter
+ * (dst[rows[i]] = src[i]) of fp32 [*, 768] rows. */
+int nbest_rows_touched(nbest_ctx* ctx, const int32_t* tokens, int T, int n_rows, int skip_row, int32_t* flags, int phase,
+                       int32_t* rows, int32_t* count, void* stream);
+int nbest_rows_move_f32(nbest_ctx* ctx, const float* src, const int32_t* rows, int n, int hidden, float* dst, int scatter,
+                        void* stream);
 
 /* ---- K1: embedding gather + LayerNorm (+dropout) ---------------------------------------------------------- */
 /* BertEmbeddings.forward (transformers/models/bert/modeling_bert.py:102-112), called from models/model.py:43-45.

@@ -42,6 +42,8 @@ _SIGNATURES = {
     "nbest_rows_gather": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]),
     "nbest_rows_scatter": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "nbest_zero": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "nbest_rows_touched": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
+    "nbest_rows_move_f32": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]),
     "nbest_embed_ln_fwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _f32, C.c_int, _vp, _vp, _vp,
                                      _f32, _u32, _vp]),
     "nbest_embed_ln_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _f32, _u32,

@@ -756,6 +756,85 @@ __global__ void rows_scatter_kernel(const __nv_bfloat16* __restrict__ src, const
   for (int c = 0; c < CPL; ++c) dp[lane + 32 * c] = __ldg(sp + lane + 32 * c);
 }
 
+// ---- row-sparse exchange of the word-embedding gradient (data parallel, large vocabularies) ----------------------------
+// Only rows whose token occurred in this step's batch carry a non-zero gradient (<= T of XLM-R's 250,002 rows): the ranks
+// agree on the union of touched rows (flags, MAX-reduced), exchange those rows as one dense [n, 768] all-reduce and
+// scatter the sums back. Ascending row order on every rank -> identical summation order -> replicas stay bit-identical.
+__global__ void rows_mark_kernel(const int32_t* __restrict__ tokens, int T, int32_t* __restrict__ flags) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) flags[tokens[t]] = 1;
+}
+// rows[0 .. count) = ascending indices r != skip_row with flags[r] != 0 (single block: chunked ballot scan)
+__global__ void __launch_bounds__(1024)
+rows_compact_kernel(const int32_t* __restrict__ flags, int n_rows, int skip_row, int32_t* __restrict__ rows, int32_t* __restrict__ count) {
+  __shared__ int warp_cnt[32];
+  __shared__ int base_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  for (int r0 = 0; r0 < n_rows; r0 += 1024) {
+    const int r = r0 + threadIdx.x;
+    const bool on = r < n_rows && r != skip_row && flags[r] != 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int off = base_s;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    if (on) rows[off + __popc(m & ((1u << lane) - 1u))] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += warp_cnt[w];
+      base_s += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base_s;
+}
+// fp32 [*, 768] rows: gather dst[i] = src[rows[i]], or scatter dst[rows[i]] = src[i]; one warp per row, float4 chunks
+__global__ void rows_move_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ rows, int n,
+                                     float* __restrict__ dst, int scatter) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t r = rows[i];
+  const float4* sp = reinterpret_cast<const float4*>(src + (scatter ? (int64_t)i : r) * H);
+  float4* dp = reinterpret_cast<float4*>(dst + (scatter ? r : (int64_t)i) * H);
+#pragma unroll
+  for (int c = 0; c < VPL; ++c) dp[lane + 32 * c] = __ldg(sp + lane + 32 * c);
+}
+
+extern "C" int nbest_rows_touched(nbest_ctx* ctx, const int32_t* tokens, int T, int n_rows, int skip_row, int32_t* flags,
+                                  int phase, int32_t* rows, int32_t* count, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, flags && n_rows > 0, "null pointer");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (phase == 0) {           // flags = 0; flags[tokens[t]] = 1
+    NBEST_CHECK_ARG(ctx, tokens && T >= 0, "null pointer");
+    NBEST_CHECK_CUDA(ctx, cudaMemsetAsync(flags, 0, sizeof(int32_t) * (size_t)n_rows, s));
+    if (T > 0) {
+      rows_mark_kernel<<<(T + 255) / 256, 256, 0, s>>>(tokens, T, flags);
+      NBEST_CHECK_LAUNCH(ctx);
+    }
+  } else {                    // rows / count from the (reduced) flags
+    NBEST_CHECK_ARG(ctx, rows && count, "null pointer");
+    rows_compact_kernel<<<1, 1024, 0, s>>>(flags, n_rows, skip_row, rows, count);
+    NBEST_CHECK_LAUNCH(ctx);
+  }
+  return NBEST_OK;
+}
+
+extern "C" int nbest_rows_move_f32(nbest_ctx* ctx, const float* src, const int32_t* rows, int n, int hidden, float* dst,
+                                   int scatter, void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  NBEST_CHECK_ARG(ctx, hidden == H, "hidden must be 768");
+  NBEST_CHECK_ARG(ctx, src && rows && dst, "null pointer");
+  if (n <= 0) return NBEST_OK;
+  rows_move_f32_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, rows, n, dst, scatter);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
 extern "C" int nbest_rows_gather(nbest_ctx* ctx, const void* src_bf16, const int32_t* row_idx, int n, int hidden, void* dst,
                                  int dst_is_f32, void* stream) {
   if (!ctx) return NBEST_EINVAL;

@@ -454,6 +454,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
         s, dev = self.spec, self.device
         pk, p_h, p_a = sv.pk, sv.p_h, sv.p_a
         T = pk.T
+        self._last_pk, self._last_T_act = pk, T_act      # (the trainer's row-sparse embedding-gradient exchange reads the token list)
         bf = lambda *shape: torch.empty(shape, device=dev, dtype=torch.bfloat16)
         kv = pk.key_valid if s.roberta_style else None
         cu = pk.cu_seqlens[:B_act + 1]

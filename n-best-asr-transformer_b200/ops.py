@@ -49,6 +49,25 @@ class _Timed:
         return False
 
 
+class _NoTimed:
+    __slots__ = ()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOTIMED = _NoTimed()
+
+
+def _timed(name, flops=0.0, nbytes=0.0, meta=None):
+    """Per-launch CUDA-event bracket while ops.profile_start() is active, a shared no-op object otherwise (the wrappers
+    run ~250 times per step: at the reference's batch 16 the step is bound by this host code, not by the GPU)."""
+    return _NOTIMED if _PROF is None else _Timed(name, flops, nbytes, meta)
+
+
 def _ctx(t):
     if not t.is_cuda:
         raise RuntimeError("nbest_b200 ops need CUDA tensors (no CPU fallback)")
@@ -65,7 +84,7 @@ def bind_stream():
     """Cache torch's current stream for the launches that follow. The model / trainer entry points call this once per
     step; code that switches streams in between must call it again (or `unbind_stream()` to query torch every time)."""
     global _STREAM
-    _STREAM = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _STREAM = torch.cuda.current_stream().cuda_stream
 
 
 def unbind_stream():
@@ -77,7 +96,7 @@ class on_stream:
     """Context manager: launches made inside go to `stream` (a torch.cuda.Stream), whatever stream the step is bound to."""
 
     def __init__(self, stream):
-        self.handle = C.c_void_p(stream.cuda_stream)
+        self.handle = stream.cuda_stream
 
     def __enter__(self):
         global _STREAM
@@ -107,11 +126,11 @@ def with_bound_stream(fn):
 
 
 def _stream():
-    return _STREAM if _STREAM is not None else C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return _STREAM if _STREAM is not None else torch.cuda.current_stream().cuda_stream
 
 
 def _p(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    return t.data_ptr() if t is not None else None      # ctypes converts int / None for c_void_p parameters
 
 
 def _check_bf16(t, name):
@@ -139,7 +158,7 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, epilogue=EPI_NONE, bias=No
                           dtype=torch.float32 if epilogue == EPI_ACCUM_F32 else torch.bfloat16)
     ctx = _ctx(a)
     kind = "gemm_wgrad" if a_mn_major else ("gemm_dgrad" if b_mn_major else "gemm_fwd")
-    with _Timed(kind, 2.0 * M * N * K, 0.0, (M, N, K, int(epilogue))):
+    with _timed(kind, 2.0 * M * N * K, 0.0, (M, N, K, int(epilogue))):
         rc = _lib.lib().nbest_gemm_bf16(
             ctx.handle, _p(a), a.stride(0), int(a_mn_major), _p(b), b.stride(0), int(b_mn_major), _p(out), out.stride(0),
             M, N, K, int(epilogue), _p(bias), _p(aux), aux.stride(0) if aux is not None else 0, _p(out2), float(p_drop),
@@ -189,7 +208,7 @@ def pack_batch(ids, seg_ids=None, kind="bert", lens_host=None):
     pk.seq_of = torch.empty(cap, dtype=torch.int32, device=dev)
     pk.key_valid = torch.empty(cap, dtype=torch.uint8, device=dev)
     ctx = _ctx(ids)
-    with _Timed('pack_batch', 0.0, 0.0):
+    with _timed('pack_batch', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_pack_batch(ctx.handle, _p(ids), _p(seg_ids), B, S, 1 if kind == "xlm-roberta" else 0,
                                               _p(pk.lens), _p(pk.cu_seqlens), _p(pk.tokens), _p(pk.seg), _p(pk.pos),
                                               _p(pk.seq_of), _p(pk.key_valid), _stream()))
@@ -238,7 +257,7 @@ def pack_batch_dual(ids_a, seg_a, lens_a, ids_t, seg_t, lens_t, kind="bert"):
     w8 = torch.empty(2 * cap, dtype=torch.uint8, device=dev)
     pk.seg, pk.key_valid = w8[:cap], w8[cap:]
     ctx = _ctx(ids_a)
-    with _Timed('pack_batch', 0.0, 0.0):
+    with _timed('pack_batch', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_pack_batch_dual(ctx.handle, _p(ids_a), _p(seg_a), Ba, Sa, _p(ids_t), _p(seg_t), Bt, St,
                                                    1 if kind == "xlm-roberta" else 0, _p(pk.lens), _p(pk.cu_seqlens),
                                                    _p(pk.tokens), _p(pk.seg), _p(pk.pos), _p(pk.seq_of), _p(pk.key_valid),
@@ -266,7 +285,7 @@ def rows_gather(src, row_idx, n, out):
     """out[i] = src[row_idx[i]] for [*, 768] bf16 rows; out may be bf16 or fp32 (see nbest_rows_gather)."""
     ctx = _ctx(src)
     _check_bf16(src, "src")
-    with _Timed('rows_gather', 0.0, 0.0):
+    with _timed('rows_gather', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_rows_gather(ctx.handle, _p(src), _p(row_idx), int(n), src.shape[1], _p(out),
                                                int(out.dtype == torch.float32), _stream()))
     return out
@@ -276,7 +295,7 @@ def rows_scatter(src, row_idx, n, T, out):
     """out [T, 768] bf16 = 0 except out[row_idx[i]] = src[i] (see nbest_rows_scatter)."""
     ctx = _ctx(src)
     _check_bf16(src, "src")
-    with _Timed('rows_scatter', 0.0, 0.0):
+    with _timed('rows_scatter', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_rows_scatter(ctx.handle, _p(src), _p(row_idx), int(n), int(T), src.shape[1], _p(out), _stream()))
     return out
 
@@ -288,12 +307,29 @@ def zero_(t):
     return t
 
 
+def rows_mark(tokens, T, flags):
+    """flags[:] = 0; flags[tokens[t]] = 1 for t < T (int32 flags over the embedding rows; see nbest_rows_touched)."""
+    ctx = _ctx(flags)
+    ctx.check(_lib.lib().nbest_rows_touched(ctx.handle, _p(tokens), int(T), flags.numel(), -1, _p(flags), 0, None, None, _stream()))
+
+
+def rows_compact(flags, skip_row, rows, count):
+    """rows[0..count) = ascending indices of set flags, skip_row excluded; count is a 1-element int32 device tensor."""
+    ctx = _ctx(flags)
+    ctx.check(_lib.lib().nbest_rows_touched(ctx.handle, None, 0, flags.numel(), int(skip_row), _p(flags), 1, _p(rows), _p(count), _stream()))
+
+
+def rows_move_f32(src, rows, n, dst, scatter):
+    ctx = _ctx(src)
+    ctx.check(_lib.lib().nbest_rows_move_f32(ctx.handle, _p(src), _p(rows), int(n), src.shape[1], _p(dst), int(bool(scatter)), _stream()))
+
+
 def pack_hyp_ids(pk, sep_id, B=None):
     """uint8 [T] hypothesis index of every packed token (see nbest_pack_hyp_ids): 0 = [CLS] + system turn + first [SEP]."""
     B = pk.B if B is None else B
     out = torch.empty(max(pk.T, 1), dtype=torch.uint8, device=pk.tokens.device)
     ctx = _ctx(pk.tokens)
-    with _Timed('pack_hyp_ids', 0.0, 0.0):
+    with _timed('pack_hyp_ids', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_pack_hyp_ids(ctx.handle, _p(pk.tokens), _p(pk.cu_seqlens), B, int(sep_id), _p(out), _stream()))
     return out[:pk.T]
 
@@ -301,7 +337,7 @@ def pack_hyp_ids(pk, sep_id, B=None):
 # ---------------------------------------------------------------------------------------------------------- embed / LN
 def embed_ln_fwd(pk, word, posemb, type_emb, gamma, beta, eps, y, mean, rstd, p_drop=0.0, seed=0):
     ctx = _ctx(word)
-    with _Timed('embed_ln_fwd', 0.0, pk.T * (3 * 768 * 4 + 768 * 2.0)):
+    with _timed('embed_ln_fwd', 0.0, pk.T * (3 * 768 * 4 + 768 * 2.0)):
         ctx.check(_lib.lib().nbest_embed_ln_fwd(ctx.handle, _p(pk.tokens), _p(pk.seg), _p(pk.pos), pk.T, _p(word), _p(posemb),
                                                 _p(type_emb), _p(gamma), _p(beta), float(eps), word.shape[1], _p(y), _p(mean),
                                                 _p(rstd), float(p_drop), _seed(seed), _stream()))
@@ -310,7 +346,7 @@ def embed_ln_fwd(pk, word, posemb, type_emb, gamma, beta, eps, y, mean, rstd, p_
 def embed_ln_bwd(pk, word, posemb, type_emb, gamma, mean, rstd, dy, dword, dpos, dtype, dgamma, dbeta, p_drop=0.0, seed=0,
                  word_pad_row=-1, pos_pad_row=-1, T=None):
     ctx = _ctx(word)
-    with _Timed('embed_ln_bwd', 0.0, (pk.T if T is None else T) * (3 * 768 * 4 + 768 * 2 + 3 * 768 * 4.0)):
+    with _timed('embed_ln_bwd', 0.0, (pk.T if T is None else T) * (3 * 768 * 4 + 768 * 2 + 3 * 768 * 4.0)):
         ctx.check(_lib.lib().nbest_embed_ln_bwd(ctx.handle, _p(pk.tokens), _p(pk.seg), _p(pk.pos), pk.T if T is None else T,
                                                 _p(word), _p(posemb), _p(type_emb), _p(gamma), _p(mean), _p(rstd), word.shape[1],
                                                 _p(dy), float(p_drop), _seed(seed), _p(dword), _p(dpos), _p(dtype), _p(dgamma),
@@ -326,14 +362,14 @@ def ln_fwd(x, gamma, beta, eps, y, mean=None, rstd=None, T=None, row_partials=No
         if row_partials.dtype != torch.float32 or not row_partials.is_contiguous() or row_partials.dim() != 3:
             raise ValueError("row_partials must be a contiguous fp32 [T, n, 2] tensor")
         n_part = row_partials.shape[1]
-    with _Timed('ln_fwd', 0.0, (x.shape[0] if T is None else T) * (2 * 768 * 2.0)):
+    with _timed('ln_fwd', 0.0, (x.shape[0] if T is None else T) * (2 * 768 * 2.0)):
         ctx.check(_lib.lib().nbest_ln_fwd_stats(ctx.handle, _p(x), _p(gamma), _p(beta), float(eps), x.shape[0] if T is None else T,
                                                 x.shape[1], _p(row_partials), n_part, _p(y), _p(mean), _p(rstd), _stream()))
 
 
 def ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dx_masked=None, dbias=None, p_drop=0.0, seed=0, T=None):
     ctx = _ctx(x)
-    with _Timed('ln_bwd', 0.0, (x.shape[0] if T is None else T) * ((3 + (dx_masked is not None)) * 768 * 2.0)):
+    with _timed('ln_bwd', 0.0, (x.shape[0] if T is None else T) * ((3 + (dx_masked is not None)) * 768 * 2.0)):
         ctx.check(_lib.lib().nbest_ln_bwd(ctx.handle, _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma),
                                           x.shape[0] if T is None else T, x.shape[1], _p(dx), _p(dx_masked), float(p_drop),
                                           _seed(seed), _p(dgamma), _p(dbeta), _p(dbias), _stream()))
@@ -341,13 +377,13 @@ def ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dx_masked=None, dbias=No
 
 def colsum(x, out, T=None):
     ctx = _ctx(x)
-    with _Timed('colsum_bf16', 0.0, (x.shape[0] if T is None else T) * x.shape[1] * 2.0):
+    with _timed('colsum_bf16', 0.0, (x.shape[0] if T is None else T) * x.shape[1] * 2.0):
         ctx.check(_lib.lib().nbest_colsum_bf16(ctx.handle, _p(x), x.shape[0] if T is None else T, x.shape[1], _p(out), _stream()))
 
 
 def cast_f32_bf16(src, dst):
     ctx = _ctx(src)
-    with _Timed('cast_f32_bf16', 0.0, src.numel() * 6.0):
+    with _timed('cast_f32_bf16', 0.0, src.numel() * 6.0):
         ctx.check(_lib.lib().nbest_cast_f32_bf16(ctx.handle, _p(src), _p(dst), src.numel(), _stream()))
 
 
@@ -366,7 +402,7 @@ def attn_fwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out, lse, p_drop=
     """min_len > 0: only sequences of at least that many tokens (the rest belongs to attn_tiles_fwd)."""
     ctx = _ctx(qkv)
     fl, by = _attn_cost(T, sum_l2, heads) if (sum_l2 and not min_len) else (0.0, 0.0)
-    with _Timed('attn_varlen_fwd', fl, by):
+    with _timed('attn_varlen_fwd', fl, by):
         ctx.check(_lib.lib().nbest_attn_varlen_fwd2(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
                                                     _p(out), _p(lse), float(p_drop), _seed(seed), int(min_len), _stream()))
 
@@ -375,7 +411,7 @@ def attn_bwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out, dout, lse, d
              T_active=None, min_len=0, sum_l2=0.0):
     ctx = _ctx(qkv)
     fl, by = _attn_cost(T, sum_l2, heads, True, T_active) if (sum_l2 and not min_len) else (0.0, 0.0)
-    with _Timed('attn_varlen_bwd', fl, by):
+    with _timed('attn_varlen_bwd', fl, by):
         ctx.check(_lib.lib().nbest_attn_varlen_bwd2(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
                                                     T if T_active is None else T_active, _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta_ws), float(p_drop), _seed(seed),
                                                     int(min_len), _stream()))
@@ -396,7 +432,7 @@ def attn_plan(cu_seqlens, seq_of, B, T, break_at=None):
     pl.row_bounds = torch.empty(2 * max(T, 1), dtype=torch.int32, device=dev)
     pl.max_tiles = B
     ctx = _ctx(cu_seqlens)
-    with _Timed('attn_plan', 0.0, 0.0):
+    with _timed('attn_plan', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_attn_plan(ctx.handle, _p(cu_seqlens), _p(seq_of), B, T, B if break_at is None else break_at,
                                              _p(pl.tiles), _p(pl.counts), _p(pl.row_bounds), _stream()))
     return pl
@@ -407,7 +443,7 @@ def attn_tiles_fwd(qkv, plan, count_idx, key_valid, heads, T, out, lse, p_drop=0
     ctx = _ctx(qkv)
     _check_bf16(qkv, "qkv")
     fl, by = _attn_cost(T, sum_l2, heads) if sum_l2 else (0.0, 0.0)
-    with _Timed('attn_tiles_fwd', fl, by):
+    with _timed('attn_tiles_fwd', fl, by):
         ctx.check(_lib.lib().nbest_attn_tiles_fwd(ctx.handle, _p(qkv), _p(plan.tiles), _p(plan.counts), int(count_idx),
                                                   plan.max_tiles, _p(plan.row_bounds), _p(key_valid), heads, T, _p(out), _p(lse),
                                                   float(p_drop), _seed(seed), _stream()))
@@ -419,7 +455,7 @@ def attn_tiles_bwd(qkv, plan, count_idx, key_valid, heads, T, T_active, dout, ls
     _check_bf16(qkv, "qkv")
     _check_bf16(dout, "dout")
     fl, by = _attn_cost(T, sum_l2, heads, True, T_active) if sum_l2 else (0.0, 0.0)
-    with _Timed('attn_tiles_bwd', fl, by):
+    with _timed('attn_tiles_bwd', fl, by):
         ctx.check(_lib.lib().nbest_attn_tiles_bwd(ctx.handle, _p(qkv), _p(plan.tiles), _p(plan.counts), int(count_idx),
                                                   plan.max_tiles, _p(plan.row_bounds), _p(key_valid), heads, T, T_active, _p(dout),
                                                   _p(lse), _p(delta), int(delta_pitch), _p(dqkv), float(p_drop), _seed(seed),
@@ -429,7 +465,7 @@ def attn_tiles_bwd(qkv, plan, count_idx, key_valid, heads, T, T_active, dout, ls
 def attn_cls_fwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out_cls, lse_cls, p_drop=0.0, seed=0):
     """Last-layer attention for the CLS query row of each of the B sequences (see nbest_attn_cls_fwd)."""
     ctx = _ctx(qkv)
-    with _Timed('attn_cls_fwd', 0.0, 0.0):
+    with _timed('attn_cls_fwd', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_attn_cls_fwd(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
                                                 _p(out_cls), _p(lse_cls), float(p_drop), _seed(seed), _stream()))
 
@@ -437,7 +473,7 @@ def attn_cls_fwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out_cls, lse_
 def attn_cls_bwd(qkv, cu_seqlens, key_valid, B, max_len, heads, T, out_cls, dout_cls, lse_cls, lse_stride, dqkv, p_drop=0.0,
                  seed=0):
     ctx = _ctx(qkv)
-    with _Timed('attn_cls_bwd', 0.0, 0.0):
+    with _timed('attn_cls_bwd', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_attn_cls_bwd(ctx.handle, _p(qkv), _p(cu_seqlens), _p(key_valid), B, max_len, heads, T,
                                                 _p(out_cls), _p(dout_cls), _p(lse_cls), lse_stride, _p(dqkv), float(p_drop),
                                                 _seed(seed), _stream()))
@@ -482,7 +518,7 @@ class DeviceHierarchy:
 
 def stc_head_fwd(x, cu_seqlens, B, W, bias, hier, cls, logits, top, bottom, final, decode=None, p_drop=0.0, seed=0):
     ctx = _ctx(x)
-    with _Timed('stc_head_fwd', 0.0, 0.0):
+    with _timed('stc_head_fwd', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_stc_head_fwd(ctx.handle, _p(x), _p(cu_seqlens), B, x.shape[1], _p(W), _p(bias), hier.ref(),
                                                 _p(hier.none_col), float(p_drop), _seed(seed), _p(cls), _p(logits), _p(top),
                                                 _p(bottom), _p(final), _p(decode), _stream()))
@@ -491,7 +527,7 @@ def stc_head_fwd(x, cu_seqlens, B, W, bias, hier, cls, logits, top, bottom, fina
 def stc_loss_fwd_bwd(logits, labels, hier, losses, dlogits, asr_cls=None, trans_cls=None, mse_scale=1.0, d_asr=None,
                      d_trans=None):
     ctx = _ctx(logits)
-    with _Timed('stc_loss_fwd_bwd', 0.0, 0.0):
+    with _timed('stc_loss_fwd_bwd', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_stc_loss_fwd_bwd(ctx.handle, _p(logits), _p(labels), logits.shape[0], hier.ref(), _p(asr_cls),
                                                     _p(trans_cls), asr_cls.shape[1] if asr_cls is not None else 768,
                                                     float(mse_scale), _p(losses), _p(dlogits), _p(d_asr), _p(d_trans), _stream()))
@@ -499,14 +535,14 @@ def stc_loss_fwd_bwd(logits, labels, hier, losses, dlogits, asr_cls=None, trans_
 
 def stc_scores_bwd(top, bottom, d_top, d_bottom, d_final, hier, dlogits):
     ctx = _ctx(top)
-    with _Timed('stc_scores_bwd', 0.0, 0.0):
+    with _timed('stc_scores_bwd', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_stc_scores_bwd(ctx.handle, _p(top), _p(bottom), _p(d_top), _p(d_bottom), _p(d_final),
                                                   top.shape[0], hier.ref(), _p(dlogits), _stream()))
 
 
 def stc_head_bwd(dlogits, cls, W, hier, dW, dbias, dcls, accumulate_dcls=False, p_drop=0.0, seed=0):
     ctx = _ctx(cls)
-    with _Timed('stc_head_bwd', 0.0, 0.0):
+    with _timed('stc_head_bwd', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_stc_head_bwd(ctx.handle, _p(dlogits), _p(cls), _p(W), cls.shape[0], cls.shape[1], hier.ref(),
                                                 float(p_drop), _seed(seed), _p(dW), _p(dbias), _p(dcls), int(accumulate_dcls),
                                                 _stream()))
@@ -517,14 +553,14 @@ def stc_metrics(decode, labels, counters, col_mask=None):
     ctx = _ctx(decode)
     assert decode.dtype == torch.uint8 and labels.dtype == torch.float32 and counters.dtype == torch.int64
     assert decode.is_contiguous() and labels.is_contiguous() and decode.shape == labels.shape
-    with _Timed('stc_metrics', 0.0, 0.0):
+    with _timed('stc_metrics', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_stc_metrics(ctx.handle, _p(decode), _p(labels), _p(col_mask), decode.shape[0],
                                                decode.shape[1], _p(counters), _stream()))
 
 
 def cls_scatter(dcls, cu_seqlens, B, T, dx):
     ctx = _ctx(dcls)
-    with _Timed('cls_scatter', 0.0, 0.0):
+    with _timed('cls_scatter', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_cls_scatter(ctx.handle, _p(dcls), _p(cu_seqlens), B, T, dcls.shape[1], _p(dx), _stream()))
 
 
@@ -533,7 +569,7 @@ def bertadam_step(p, g, m, v, p_bf16, tensors_dev, n_tensors, chunks_dev, n_chun
                   eps=1e-6, max_grad_norm=1.0, mode=_lib.ADAM_BERT, global_clip=False, step=0):
     """mode ADAM_BERT: nbest_bertadam_step semantics; ADAM_HF_ADAMW / ADAM_TORCH: see nbest_adam_step."""
     ctx = _ctx(p)
-    with _Timed('bertadam_step', 0.0, 0.0):
+    with _timed('bertadam_step', 0.0, 0.0):
         ctx.check(_lib.lib().nbest_adam_step(ctx.handle, int(mode), _p(p), _p(g), _p(m), _p(v), _p(p_bf16), _p(tensors_dev),
                                              n_tensors, _p(chunks_dev), n_chunks, _p(norms_ws), float(sched), float(b1),
                                              float(b2), float(eps), float(max_grad_norm), int(bool(global_clip)), int(step),

@@ -149,6 +149,20 @@ class DataParallelTrainer:
             from . import _lib
             _lib.context(model.device.index).set_gemm_dynamic(self.world > 1)
         self._bucket_names = {n for n, _, _ in segments}
+        # Word-embedding gradient: of the V x 768 table only the rows of tokens that occurred in the batch are non-zero
+        # (<= T of XLM-R's 250,002). For large tables the ranks exchange the union of touched rows as one compact
+        # all-reduce instead of the dense table (768 MB fp32 for XLM-R: the un-overlappable tail of the step, since the
+        # embedding gradient is the last thing backward produces). Exact: untouched rows are zero on every rank.
+        env_sp = os.environ.get("NBEST_SPARSE_EMB")
+        big = model.spec.vocab_size * 768 * 4 >= (256 << 20)
+        self.sparse_emb = self.world > 1 and model.flat.grads.is_cuda and ((env_sp != "0") if env_sp is not None else big) \
+            and (env_sp == "1" or big)
+        if self.sparse_emb:
+            V = model.spec.vocab_size
+            self._sp_flags = torch.zeros(V, dtype=torch.int32, device=model.device)
+            self._sp_rows = torch.empty(V, dtype=torch.int32, device=model.device)
+            self._sp_count = torch.zeros(1, dtype=torch.int32, device=model.device)
+            self._sp_buf = None
         if self.overlap_optimizer:
             optimizer.set_buckets(segments)
             self.opt_stream = torch.cuda.Stream(device=model.device)
@@ -167,8 +181,44 @@ class DataParallelTrainer:
         if name != "slot":
             self._launch_bucket(name)
 
+    def _reduce_emb_sparse(self):
+        """Row-sparse SUM of the word-embedding gradient + dense SUM of the rest of the embedding bucket, on the comm stream."""
+        m, f = self.model, self.model.flat
+        V = m.spec.vocab_size
+        w0 = f.offsets[m._index["bert_encoder.embeddings.word_embeddings.weight"]]
+        s, e = self.bucketer.by_name["emb"]
+        assert s <= w0 and w0 + V * 768 <= e
+        gw = f.grads[w0:w0 + V * 768].view(V, 768)
+        pk, T_act = m._last_pk, m._last_T_act
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            with ops.on_stream(self.comm_stream):
+                ops.rows_mark(pk.tokens, T_act, self._sp_flags)
+            dist.all_reduce(self._sp_flags, op=dist.ReduceOp.MAX, group=self.group)
+            with ops.on_stream(self.comm_stream):
+                ops.rows_compact(self._sp_flags, m.spec.pad_token_id, self._sp_rows, self._sp_count)
+            n = int(self._sp_count.item())               # the one host read: sizes the compact exchange
+            if n > 0:
+                if self._sp_buf is None or self._sp_buf.shape[0] < n:
+                    self._sp_buf = torch.empty((max(n, 4096) * 5 // 4, 768), dtype=torch.float32, device=m.device)
+                buf = self._sp_buf[:n]
+                with ops.on_stream(self.comm_stream):
+                    ops.rows_move_f32(gw, self._sp_rows, n, buf, scatter=False)
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+                with ops.on_stream(self.comm_stream):
+                    ops.rows_move_f32(buf, self._sp_rows, n, gw, scatter=True)
+            for a, b in ((s, w0), (w0 + V * 768, e)):
+                if b > a:
+                    dist.all_reduce(f.grads[a:b], op=dist.ReduceOp.SUM, group=self.group)
+        self.last_sparse_rows = n
+
     def _launch_bucket(self, name):
-        self.bucketer.reduce(name)                       # DP: all-reduce on the comm stream after what is enqueued so far
+        if name == "emb" and self.sparse_emb and getattr(self.model, "_last_pk", None) is not None:
+            self._reduce_emb_sparse()
+        else:
+            self.bucketer.reduce(name)                   # DP: all-reduce on the comm stream after what is enqueued so far
         if not self.overlap_optimizer or name not in self._bucket_names:
             return
         ev = torch.cuda.Event()

@@ -8,7 +8,8 @@ attention-backward slots, per-bucket BertAdam on the side stream, --add_l2_loss 
 per-tensor clipping after the reduce). Rank 0 then repeats the same steps on ONE GPU with the concatenated batch and
 no collective, and the post-step weights must agree:  the parameter displacement after 3 optimizer steps has cosine
 >= 0.999 per bucket-sized block against the single-GPU run and the same length within 2 %, the loss terms (all-reduced)
-agree to 1e-3. Dropout is off (ranks draw independent masks by design). Prints one PASS / FAIL line per check.
+agree to 1e-3. Dropout is off (ranks draw independent masks by design). Prints one PASS / FAIL line per check. NBEST_SPARSE_EMB=1 forces
+the row-sparse exchange of the word-embedding gradient (default only for XLM-R-sized tables) through the same checks.
 """
 import json
 import os
@@ -60,12 +61,16 @@ def main():
     model, optim = build()
     init = model.flat.params.clone()
     trainer = DataParallelTrainer(model, optim, add_l2_loss=True)
+    if rank == 0:
+        print("INFO row-sparse embedding-gradient exchange: %s (NBEST_SPARSE_EMB=%s)" % (trainer.sparse_emb, os.environ.get("NBEST_SPARSE_EMB")))
     dp_losses = []
     for s in range(steps):
         d = trim(batches[s], slice(rank * per_rank, (rank + 1) * per_rank))
         losses = trainer.step(d["ids"], d["labels"], d["trans_ids"], d["seg"], d["trans_seg"])
         dp_losses.append(trainer.global_losses(losses).clone())
     torch.cuda.synchronize()
+    if rank == 0 and trainer.sparse_emb:
+        print("INFO rows exchanged in the last step: %d of %d" % (trainer.last_sparse_rows, model.spec.vocab_size))
     dp_params = model.flat.params.clone()
     # every rank must hold the same replica
     chk = torch.stack([dp_params.double().sum(), dp_params.double().abs().sum()])

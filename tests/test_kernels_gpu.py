@@ -753,3 +753,33 @@ def test_hypothesis_id_map_bit_exact():
             seg = tok[cu[b]:cu[b + 1]] == sep
             exp[cu[b]:cu[b + 1]] = np.minimum(255, np.concatenate([[0], np.cumsum(seg)[:-1]]))
         assert np.array_equal(got, exp), kind
+
+
+def test_row_sparse_embedding_exchange_kernels():
+    """mark / compact / gather / scatter of the data-parallel trainer's row-sparse embedding-gradient exchange."""
+    from nbest_b200 import ops
+    V, T = 250002, 9000
+    g = torch.Generator(device="cuda").manual_seed(2)
+    tokens = torch.randint(0, V, (T + 500,), device="cuda", generator=g, dtype=torch.int32)
+    tokens[::7] = 1                                              # <pad> = padding_idx occurs often and is skipped
+    flags = torch.full((V,), 9, dtype=torch.int32, device="cuda")
+    ops.rows_mark(tokens, T, flags)
+    exp = torch.zeros(V, dtype=torch.int32, device="cuda")
+    exp[tokens[:T].long()] = 1
+    assert torch.equal(flags, exp)
+    rows = torch.empty(V, dtype=torch.int32, device="cuda")
+    count = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.rows_compact(flags, 1, rows, count)
+    ref = torch.nonzero(exp).flatten().int()
+    ref = ref[ref != 1]
+    n = int(count.item())
+    assert n == ref.numel() and torch.equal(rows[:n], ref)
+    table = torch.randn(V, H, device="cuda", generator=g)
+    buf = torch.empty(n, H, device="cuda")
+    ops.rows_move_f32(table, rows, n, buf, scatter=False)
+    assert torch.equal(buf, table[ref.long()])
+    out = torch.zeros_like(table)
+    ops.rows_move_f32(buf * 2, rows, n, out, scatter=True)
+    chk = torch.zeros_like(table)
+    chk[ref.long()] = table[ref.long()] * 2
+    assert torch.equal(out, chk)
