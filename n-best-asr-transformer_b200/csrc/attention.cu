@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu, const uint8_t* __restrict__ key_valid,
                 int heads, int T, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, float scale, uint32_t thr,
                 float rscale, uint32_t seed, int min_len) {
+  pdl_grid_sync();
   const int qb = blockIdx.x, h0 = blockIdx.y * HPC, b = blockIdx.z;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   const int q0 = qb * BLK;
@@ -261,6 +262,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict
 // ------------------------------------------------------------------------------------------------ backward: delta
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, int rows,
                                   int T, int heads, float* __restrict__ delta) {
+  pdl_grid_sync();
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -292,6 +294,7 @@ attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __res
                      const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
                      const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
                      float scale, uint32_t thr, float rscale, uint32_t seed, int dpitch, int min_len) {
+  pdl_grid_sync();
   const int kb = blockIdx.x, h0 = blockIdx.y * HPC, b = blockIdx.z;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   const int k0 = kb * BLK;
@@ -414,6 +417,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restr
                    const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
                    float scale, uint32_t thr, float rscale, uint32_t seed, int dpitch, int min_len) {
+  pdl_grid_sync();
   const int qb = blockIdx.x, h0 = blockIdx.y * HPC, b = blockIdx.z;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   const int q0 = qb * BLK;
@@ -541,6 +545,7 @@ attn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __re
                       const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
                       const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
                       float scale, uint32_t thr, float rscale, uint32_t seed, int dpitch) {
+  pdl_grid_sync();
   const int h0 = blockIdx.x * HPC, b = blockIdx.y;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   if (L <= 0 || L > BLK) return;               // longer sequences: attn_bwd_dkdv_kernel + attn_bwd_dq_kernel
@@ -735,10 +740,10 @@ extern "C" int nbest_attn_varlen_fwd2(nbest_ctx* ctx, const void* qkv_bf16, cons
     attr = true;
   }
   if (heads % 4 == 0)
-    attn_fwd_kernel<4><<<dim3(nqb, heads / 4, B), kThreads, sizeof(FwdSmem), s>>>(q, cu_seqlens, key_valid, heads, T, o, lse,
+    nbest_launch(attn_fwd_kernel<4>, dim3(dim3(nqb, heads / 4, B)), dim3(kThreads), sizeof(FwdSmem), s, q, cu_seqlens, key_valid, heads, T, o, lse,
                                                                               0.125f, thr, rscale, seed, min_len);
   else
-    attn_fwd_kernel<1><<<dim3(nqb, heads, B), kThreads, sizeof(FwdSmem), s>>>(q, cu_seqlens, key_valid, heads, T, o, lse, 0.125f,
+    nbest_launch(attn_fwd_kernel<1>, dim3(dim3(nqb, heads, B)), dim3(kThreads), sizeof(FwdSmem), s, q, cu_seqlens, key_valid, heads, T, o, lse, 0.125f,
                                                                           thr, rscale, seed, min_len);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
@@ -777,7 +782,7 @@ extern "C" int nbest_attn_varlen_bwd2(nbest_ctx* ctx, const void* qkv_bf16, cons
   // out-projection dgrad GEMM, NBEST_EPI_DELTA); otherwise it is computed here with row pitch T
   const int dpitch = o ? T : T_active;
   if (T_active > 0 && o) {
-    attn_delta_kernel<<<(T_active + 7) / 8, 256, 0, s>>>(o, g, T_active, T, heads, delta_ws);
+    nbest_launch(attn_delta_kernel, dim3((T_active + 7) / 8), dim3(256), 0, s, o, g, T_active, T, heads, delta_ws);
     NBEST_CHECK_LAUNCH(ctx);
   }
   static bool attr_dev[64] = {};   // per device: cudaFuncSetAttribute applies to the current device only
@@ -805,7 +810,7 @@ extern "C" int nbest_attn_varlen_bwd2(nbest_ctx* ctx, const void* qkv_bf16, cons
       if (rc) return rc;
       fattr_dev[ctx->device & 63] = true;
     }
-    attn_bwd_fused_kernel<4><<<dim3(heads / 4, B), kThreads, sizeof(FusedSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse,
+    nbest_launch(attn_bwd_fused_kernel<4>, dim3(dim3(heads / 4, B)), dim3(kThreads), sizeof(FusedSmem), s, q, cu_seqlens, key_valid, heads, T, g, lse,
                                                                                    delta_ws, dq, 0.125f, thr, rscale, seed, dpitch);
     NBEST_CHECK_LAUNCH(ctx);
     if (max_len <= BLK) return NBEST_OK;
@@ -815,18 +820,18 @@ extern "C" int nbest_attn_varlen_bwd2(nbest_ctx* ctx, const void* qkv_bf16, cons
   //  shorter CTAs — with 4 heads per CTA the leftover grid is less than a wave and runs at one CTA's serial latency)
   if (heads % 4 == 0 && !use_fused) {
     const dim3 grid(nb, heads / 4, B);
-    attn_bwd_dkdv_kernel<4><<<grid, kThreads, sizeof(DkdvSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq,
+    nbest_launch(attn_bwd_dkdv_kernel<4>, dim3(grid), dim3(kThreads), sizeof(DkdvSmem), s, q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq,
                                                                     0.125f, thr, rscale, seed, dpitch, min_len);
     NBEST_CHECK_LAUNCH(ctx);
-    attn_bwd_dq_kernel<4><<<grid, kThreads, sizeof(DqSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f,
+    nbest_launch(attn_bwd_dq_kernel<4>, dim3(grid), dim3(kThreads), sizeof(DqSmem), s, q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f,
                                                                 thr, rscale, seed, dpitch, min_len);
     NBEST_CHECK_LAUNCH(ctx);
   } else {
     const dim3 grid(nb, heads, B);
-    attn_bwd_dkdv_kernel<1><<<grid, kThreads, sizeof(DkdvSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq,
+    nbest_launch(attn_bwd_dkdv_kernel<1>, dim3(grid), dim3(kThreads), sizeof(DkdvSmem), s, q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq,
                                                                     0.125f, thr, rscale, seed, dpitch, min_len);
     NBEST_CHECK_LAUNCH(ctx);
-    attn_bwd_dq_kernel<1><<<grid, kThreads, sizeof(DqSmem), s>>>(q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f,
+    nbest_launch(attn_bwd_dq_kernel<1>, dim3(grid), dim3(kThreads), sizeof(DqSmem), s, q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f,
                                                                 thr, rscale, seed, dpitch, min_len);
     NBEST_CHECK_LAUNCH(ctx);
   }

@@ -44,6 +44,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 constexpr int kPlanSmemSeqs = 4096;     // sequences whose plan is built in shared memory (larger batches: serial global scan)
 __global__ void __launch_bounds__(256)
 attn_plan_kernel(const int32_t* __restrict__ cu_g, int B, int break_at, int2* __restrict__ tiles, int32_t* __restrict__ counts) {
+  pdl_grid_sync();
   __shared__ int32_t cu_s[kPlanSmemSeqs + 1];
   __shared__ int32_t nxt_s[kPlanSmemSeqs];   // first sequence that no longer fits a tile opened at sequence s (s + 1 for long ones)
   if (B <= kPlanSmemSeqs) {
@@ -124,6 +125,7 @@ attn_plan_kernel(const int32_t* __restrict__ cu_g, int B, int break_at, int2* __
 // row_bounds[t] = {first row, one-past-last row} of the sequence token t belongs to
 __global__ void attn_row_bounds_kernel(const int32_t* __restrict__ cu, const int32_t* __restrict__ seq_of, int T,
                                        int2* __restrict__ row_bounds) {
+  pdl_grid_sync();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const int s = seq_of[t];
@@ -219,6 +221,7 @@ struct FwdArgs {
 template <bool kDrop>
 __global__ void __launch_bounds__(fwd::kThreads, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdArgs a) {
+  pdl_grid_sync();
   using namespace fwd;
   extern __shared__ __align__(1024) uint8_t smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
@@ -543,6 +546,7 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 template <bool kDrop>
 __global__ void __launch_bounds__(bwd::kThreads, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const BwdArgs a) {
+  pdl_grid_sync();
   using namespace bwd;
   extern __shared__ __align__(1024) uint8_t smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
@@ -837,9 +841,9 @@ extern "C" int nbest_attn_plan(nbest_ctx* ctx, const int32_t* cu_seqlens, const 
   NBEST_CHECK_ARG(ctx, cu_seqlens && seq_of && tiles && counts && row_bounds, "null pointer");
   NBEST_CHECK_ARG(ctx, B > 0 && T > 0 && break_at >= 0 && break_at <= B, "need B > 0, T > 0, 0 <= break_at <= B");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  attn_plan_kernel<<<1, 256, 0, s>>>(cu_seqlens, B, break_at, reinterpret_cast<int2*>(tiles), counts);
+  nbest_launch(attn_plan_kernel, dim3(1), dim3(256), 0, s, cu_seqlens, B, break_at, reinterpret_cast<int2*>(tiles), counts);
   NBEST_CHECK_LAUNCH(ctx);
-  attn_row_bounds_kernel<<<(T + 255) / 256, 256, 0, s>>>(cu_seqlens, seq_of, T, reinterpret_cast<int2*>(row_bounds));
+  nbest_launch(attn_row_bounds_kernel, dim3((T + 255) / 256), dim3(256), 0, s, cu_seqlens, seq_of, T, reinterpret_cast<int2*>(row_bounds));
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
@@ -878,9 +882,9 @@ extern "C" int nbest_attn_tiles_fwd(nbest_ctx* ctx, const void* qkv_bf16, const 
   const int64_t items = (int64_t)max_tiles * heads;
   const int grid = (int)(items < ctx->num_sms ? items : ctx->num_sms);
   if (a.thr != 0u)
-    attn_tc_fwd_kernel<true><<<grid, fwd::kThreads, fwd::kSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, a);
+    nbest_launch(attn_tc_fwd_kernel<true>, dim3(grid), dim3(fwd::kThreads), fwd::kSmemBytes, reinterpret_cast<cudaStream_t>(stream), tm, a);
   else
-    attn_tc_fwd_kernel<false><<<grid, fwd::kThreads, fwd::kSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm, a);
+    nbest_launch(attn_tc_fwd_kernel<false>, dim3(grid), dim3(fwd::kThreads), fwd::kSmemBytes, reinterpret_cast<cudaStream_t>(stream), tm, a);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
@@ -927,9 +931,9 @@ extern "C" int nbest_attn_tiles_bwd(nbest_ctx* ctx, const void* qkv_bf16, const 
   const int64_t items = (int64_t)max_tiles * heads;
   const int grid = (int)(items < ctx->num_sms ? items : ctx->num_sms);
   if (a.thr != 0u)
-    attn_tc_bwd_kernel<true><<<grid, bwd::kThreads, bwd::kSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tmq, tmo, a);
+    nbest_launch(attn_tc_bwd_kernel<true>, dim3(grid), dim3(bwd::kThreads), bwd::kSmemBytes, reinterpret_cast<cudaStream_t>(stream), tmq, tmo, a);
   else
-    attn_tc_bwd_kernel<false><<<grid, bwd::kThreads, bwd::kSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tmq, tmo, a);
+    nbest_launch(attn_tc_bwd_kernel<false>, dim3(grid), dim3(bwd::kThreads), bwd::kSmemBytes, reinterpret_cast<cudaStream_t>(stream), tmq, tmo, a);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }

@@ -23,6 +23,7 @@ constexpr int kThreads = 256;
 __global__ void __launch_bounds__(kThreads)
 adam_norm_kernel(const float* __restrict__ g, const nbest_adam_tensor* __restrict__ tensors, const int32_t* __restrict__ chunks,
                  float* __restrict__ partials) {
+  pdl_grid_sync();
   const int ti = chunks[3 * blockIdx.x], start = chunks[3 * blockIdx.x + 1], len = chunks[3 * blockIdx.x + 2];
   const int64_t base = tensors[ti].offset + start;
   const float* gp = g + base;
@@ -49,6 +50,7 @@ adam_norm_kernel(const float* __restrict__ g, const nbest_adam_tensor* __restric
 __global__ void __launch_bounds__(kThreads)
 adam_norm_finish_kernel(const int32_t* __restrict__ chunks, int n_chunks, const float* __restrict__ partials,
                         float* __restrict__ norms) {
+  pdl_grid_sync();
   const int ti = blockIdx.x;
   int lo = 0, hi = n_chunks;
   while (lo < hi) {                      // first chunk with tensor index >= ti
@@ -105,6 +107,7 @@ adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
                    __nv_bfloat16* __restrict__ pb, const nbest_adam_tensor* __restrict__ tensors, int n_tensors,
                    const int32_t* __restrict__ chunks, const float* __restrict__ norms, double sched, float b1, float b2,
                    float eps, float max_grad_norm, int global_clip, float inv_bc1, float inv_sqrt_bc2) {
+  pdl_grid_sync();
   const int ti = chunks[3 * blockIdx.x], start = chunks[3 * blockIdx.x + 1], len = chunks[3 * blockIdx.x + 2];
   const nbest_adam_tensor t = tensors[ti];
   const int64_t base = t.offset + start;
@@ -169,9 +172,9 @@ extern "C" int nbest_adam_step(nbest_ctx* ctx, int mode, float* p, const float* 
                          reinterpret_cast<uintptr_t>(v)) & 15) == 0, "flat buffers must be 16-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (max_grad_norm > 0.f) {
-    adam_norm_kernel<<<n_chunks, kThreads, 0, s>>>(g, tensors, chunks, norms_ws + n_tensors);
+    nbest_launch(adam_norm_kernel, dim3(n_chunks), dim3(kThreads), 0, s, g, tensors, chunks, norms_ws + n_tensors);
     NBEST_CHECK_LAUNCH(ctx);
-    adam_norm_finish_kernel<<<n_tensors, kThreads, 0, s>>>(chunks, n_chunks, norms_ws + n_tensors, norms_ws);
+    nbest_launch(adam_norm_finish_kernel, dim3(n_tensors), dim3(kThreads), 0, s, chunks, n_chunks, norms_ws + n_tensors, norms_ws);
     NBEST_CHECK_LAUNCH(ctx);
   }
   float inv_bc1 = 1.f, inv_sqrt_bc2 = 1.f;
@@ -181,14 +184,14 @@ extern "C" int nbest_adam_step(nbest_ctx* ctx, int mode, float* p, const float* 
   }
   auto* pb = reinterpret_cast<__nv_bfloat16*>(p_bf16);
   if (mode == NBEST_ADAM_BERT)
-    adam_update_kernel<NBEST_ADAM_BERT><<<n_chunks, kThreads, 0, s>>>(p, g, m, v, pb, tensors, n_tensors, chunks, norms_ws, sched,
+    nbest_launch(adam_update_kernel<NBEST_ADAM_BERT>, dim3(n_chunks), dim3(kThreads), 0, s, p, g, m, v, pb, tensors, n_tensors, chunks, norms_ws, sched,
                                                                        b1, b2, eps, max_grad_norm, global_clip, inv_bc1, inv_sqrt_bc2);
   else if (mode == NBEST_ADAM_HF_ADAMW)
-    adam_update_kernel<NBEST_ADAM_HF_ADAMW><<<n_chunks, kThreads, 0, s>>>(p, g, m, v, pb, tensors, n_tensors, chunks, norms_ws,
+    nbest_launch(adam_update_kernel<NBEST_ADAM_HF_ADAMW>, dim3(n_chunks), dim3(kThreads), 0, s, p, g, m, v, pb, tensors, n_tensors, chunks, norms_ws,
                                                                            sched, b1, b2, eps, max_grad_norm, global_clip, inv_bc1,
                                                                            inv_sqrt_bc2);
   else
-    adam_update_kernel<NBEST_ADAM_TORCH><<<n_chunks, kThreads, 0, s>>>(p, g, m, v, pb, tensors, n_tensors, chunks, norms_ws, sched,
+    nbest_launch(adam_update_kernel<NBEST_ADAM_TORCH>, dim3(n_chunks), dim3(kThreads), 0, s, p, g, m, v, pb, tensors, n_tensors, chunks, norms_ws, sched,
                                                                         b1, b2, eps, max_grad_norm, global_clip, inv_bc1, inv_sqrt_bc2);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;

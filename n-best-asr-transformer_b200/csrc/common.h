@@ -76,6 +76,26 @@ void nbest_set_error(nbest_ctx* ctx, const char* fmt, ...);
     NBEST_CHECK_CUDA((ctx), cudaGetLastError()); \
   } while (0)
 
+// Kernel launch with programmatic dependent launch (NBEST_PDL=0 disables): the ~250 kernels of a step are short (5-100 us),
+// so the launch latency and the drain / fill bubble at every kernel boundary add up; see ptx.cuh pdl_grid_sync.
+extern int g_nbest_pdl;
+#ifdef __CUDACC__
+template <typename K, typename... Args>
+inline cudaError_t nbest_launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_nbest_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#endif
+
 // Encode a 2-D bf16 row-major tensor [rows, cols] (row pitch ld elements) with a {64 x box_rows} box, 128-B swizzle.
 int nbest_make_tmap_bf16(nbest_ctx* ctx, CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                          uint32_t box_rows);

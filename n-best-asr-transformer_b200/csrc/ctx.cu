@@ -4,6 +4,8 @@
 
 #include "common.h"
 
+int g_nbest_pdl = 1;
+
 void nbest_set_error(nbest_ctx* ctx, const char* fmt, ...) {
   if (!ctx) return;
   va_list ap;
@@ -57,6 +59,7 @@ extern "C" int nbest_ctx_create(nbest_ctx** out, int device) {
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
   };
+  g_nbest_pdl = env_int("NBEST_PDL", 1) != 0;
   ctx->knobs.gemm_cta_group = env_int("NBEST_GEMM_CTA_GROUP", 2) == 1 ? 1 : 2;
   ctx->knobs.gemm_force_bn = env_int("NBEST_GEMM_BN", 0);
   ctx->knobs.wgrad_splits = env_int("NBEST_WGRAD_SPLITS", 0);

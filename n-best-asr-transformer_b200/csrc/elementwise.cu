@@ -29,6 +29,7 @@ static inline uint32_t drop_threshold(float p) {
 
 // ------------------------------------------------------------------------------------------------ packing
 __global__ void pack_lens_kernel(const int64_t* __restrict__ ids, int B, int S, int32_t* __restrict__ lens) {
+  pdl_grid_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
   const int lane = threadIdx.x & 31;
@@ -40,6 +41,7 @@ __global__ void pack_lens_kernel(const int64_t* __restrict__ ids, int B, int S, 
 }
 
 __global__ void pack_scan_kernel(const int32_t* __restrict__ lens, int B, int32_t* __restrict__ cu) {
+  pdl_grid_sync();
   __shared__ int32_t sh[1024];
   __shared__ int32_t carry;
   if (threadIdx.x == 0) {
@@ -69,6 +71,7 @@ __global__ void pack_scatter_kernel(const int64_t* __restrict__ ids, const int64
                                     int pos_mode, const int32_t* __restrict__ cu, int32_t* __restrict__ tokens,
                                     uint8_t* __restrict__ seg, int32_t* __restrict__ pos, int32_t* __restrict__ seq_of,
                                     uint8_t* __restrict__ key_valid, int row0) {
+  pdl_grid_sync();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
   const int lane = threadIdx.x & 31;
@@ -101,6 +104,7 @@ __global__ void pack_scatter_kernel(const int64_t* __restrict__ ids, const int64
 // hyp_id[t] = number of separator tokens before position t of its sequence (one warp per sequence, ballot scan)
 __global__ void pack_hyp_ids_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ cu, int B, int sep_id,
                                     uint8_t* __restrict__ hyp_id) {
+  pdl_grid_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
   const int lane = threadIdx.x & 31;
@@ -167,6 +171,7 @@ embed_ln_fwd_kernel(const int32_t* __restrict__ tokens, const uint8_t* __restric
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                     __nv_bfloat16* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, uint32_t thr,
                     float scale, uint32_t seed) {
+  pdl_grid_sync();
   const int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (t >= T) return;
   const int lane = threadIdx.x & 31;
@@ -217,6 +222,7 @@ template <int kLnFwdRows>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kLnFwdRows <= 2 ? 4 : 2)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ xin, const float* __restrict__ gamma, const float* __restrict__ beta,
               float eps, int T, __nv_bfloat16* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int t0 = (blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * kLnFwdRows;
   if (t0 >= T) return;
@@ -275,6 +281,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 ln_fwd_stats_kernel(const __nv_bfloat16* __restrict__ xin, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float eps, int T, const float2* __restrict__ row_part, int n_part, __nv_bfloat16* __restrict__ y,
                     float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int t0 = (blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * kRows;
   if (t0 >= T) return;
@@ -334,6 +341,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 ln_fwd_stream_kernel(const __nv_bfloat16* __restrict__ xin, const float* __restrict__ gamma, const float* __restrict__ beta,
                      float eps, int T, const float2* __restrict__ row_part, int n_part, __nv_bfloat16* __restrict__ y,
                      float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_grid_sync();
   __shared__ float4 gs[CPL][2][32], bs[CPL][2][32];
   for (int idx = threadIdx.x; idx < H / 4; idx += blockDim.x) {
     const int c = 4 * idx, i = c >> 8, within = c & 255;
@@ -491,6 +499,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dyin, const __nv_bfloat16* __res
               const float* __restrict__ rstd, const float* __restrict__ gamma, int T, __nv_bfloat16* __restrict__ dx,
               __nv_bfloat16* __restrict__ dxm, uint32_t thr, float scale, uint32_t seed, float* __restrict__ dgamma,
               float* __restrict__ dbeta, float* __restrict__ dbias) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t ring = smem_u32(ln_smem) + warp * (kLnStages * kLnStageBytes);
@@ -593,6 +602,7 @@ embed_ln_bwd_kernel(const int32_t* __restrict__ tokens, const uint8_t* __restric
                     const __nv_bfloat16* __restrict__ dyin, uint32_t thr, float scale, uint32_t seed,
                     float* __restrict__ dword, float* __restrict__ dpos, float* __restrict__ dtype,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, int word_pad_row, int pos_pad_row) {
+  pdl_grid_sync();
   __shared__ float sh[kWarpsPerBlock * H];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 dgam[VPL], dbet[VPL], dty0[VPL], dty1[VPL];
@@ -649,6 +659,7 @@ embed_ln_bwd_kernel(const int32_t* __restrict__ tokens, const uint8_t* __restric
 
 // ------------------------------------------------------------------------------------------------ column sums / cast
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int T, int N, int rows_per_block, float* __restrict__ out) {
+  pdl_grid_sync();
   const int c = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   if (c >= N) return;
   const int r0 = blockIdx.y * rows_per_block;
@@ -667,6 +678,7 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int T, int N,
 }
 
 __global__ void cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  pdl_grid_sync();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
@@ -692,11 +704,11 @@ extern "C" int nbest_pack_batch(nbest_ctx* ctx, const int64_t* ids, const int64_
   NBEST_CHECK_ARG(ctx, pos_mode == 0 || pos_mode == 1, "pos_mode must be 0 (bert) or 1 (xlm-roberta)");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int blocks = (B + 7) / 8;
-  pack_lens_kernel<<<blocks, 256, 0, s>>>(ids, B, S, lens);
+  nbest_launch(pack_lens_kernel, dim3(blocks), dim3(256), 0, s, ids, B, S, lens);
   NBEST_CHECK_LAUNCH(ctx);
-  pack_scan_kernel<<<1, 1024, 0, s>>>(lens, B, cu_seqlens);
+  nbest_launch(pack_scan_kernel, dim3(1), dim3(1024), 0, s, lens, B, cu_seqlens);
   NBEST_CHECK_LAUNCH(ctx);
-  pack_scatter_kernel<<<blocks, 256, 0, s>>>(ids, seg_ids, B, S, pos_mode, cu_seqlens, tokens, seg, pos, seq_of, key_valid, 0);
+  nbest_launch(pack_scatter_kernel, dim3(blocks), dim3(256), 0, s, ids, seg_ids, B, S, pos_mode, cu_seqlens, tokens, seg, pos, seq_of, key_valid, 0);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
@@ -710,15 +722,15 @@ extern "C" int nbest_pack_batch_dual(nbest_ctx* ctx, const int64_t* ids_a, const
   NBEST_CHECK_ARG(ctx, B_a > 0 && S_a > 0 && B_t > 0 && S_t > 0, "empty batch");
   NBEST_CHECK_ARG(ctx, pos_mode == 0 || pos_mode == 1, "pos_mode must be 0 (bert) or 1 (xlm-roberta)");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  pack_lens_kernel<<<(B_a + 7) / 8, 256, 0, s>>>(ids_a, B_a, S_a, lens);
+  nbest_launch(pack_lens_kernel, dim3((B_a + 7) / 8), dim3(256), 0, s, ids_a, B_a, S_a, lens);
   NBEST_CHECK_LAUNCH(ctx);
-  pack_lens_kernel<<<(B_t + 7) / 8, 256, 0, s>>>(ids_t, B_t, S_t, lens + B_a);
+  nbest_launch(pack_lens_kernel, dim3((B_t + 7) / 8), dim3(256), 0, s, ids_t, B_t, S_t, lens + B_a);
   NBEST_CHECK_LAUNCH(ctx);
-  pack_scan_kernel<<<1, 1024, 0, s>>>(lens, B_a + B_t, cu_seqlens);
+  nbest_launch(pack_scan_kernel, dim3(1), dim3(1024), 0, s, lens, B_a + B_t, cu_seqlens);
   NBEST_CHECK_LAUNCH(ctx);
-  pack_scatter_kernel<<<(B_a + 7) / 8, 256, 0, s>>>(ids_a, seg_a, B_a, S_a, pos_mode, cu_seqlens, tokens, seg, pos, seq_of, key_valid, 0);
+  nbest_launch(pack_scatter_kernel, dim3((B_a + 7) / 8), dim3(256), 0, s, ids_a, seg_a, B_a, S_a, pos_mode, cu_seqlens, tokens, seg, pos, seq_of, key_valid, 0);
   NBEST_CHECK_LAUNCH(ctx);
-  pack_scatter_kernel<<<(B_t + 7) / 8, 256, 0, s>>>(ids_t, seg_t, B_t, S_t, pos_mode, cu_seqlens, tokens, seg, pos, seq_of, key_valid, B_a);
+  nbest_launch(pack_scatter_kernel, dim3((B_t + 7) / 8), dim3(256), 0, s, ids_t, seg_t, B_t, S_t, pos_mode, cu_seqlens, tokens, seg, pos, seq_of, key_valid, B_a);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
@@ -726,6 +738,7 @@ extern "C" int nbest_pack_batch_dual(nbest_ctx* ctx, const int64_t* ids_a, const
 // dst[i, :] = src[row_idx[i], :] (bf16 -> bf16, or bf16 -> fp32 when dst_f32); one warp per row, 16-byte chunks
 __global__ void rows_gather_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ row_idx, int n,
                                    void* __restrict__ dst, int dst_f32) {
+  pdl_grid_sync();
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= n) return;
   const int lane = threadIdx.x & 31;
@@ -747,6 +760,7 @@ __global__ void rows_gather_kernel(const __nv_bfloat16* __restrict__ src, const 
 // dst[row_idx[i], :] = src[i, :] (bf16); the caller zero-fills dst
 __global__ void rows_scatter_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ row_idx, int n,
                                     __nv_bfloat16* __restrict__ dst) {
+  pdl_grid_sync();
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= n) return;
   const int lane = threadIdx.x & 31;
@@ -761,12 +775,14 @@ __global__ void rows_scatter_kernel(const __nv_bfloat16* __restrict__ src, const
 // agree on the union of touched rows (flags, MAX-reduced), exchange those rows as one dense [n, 768] all-reduce and
 // scatter the sums back. Ascending row order on every rank -> identical summation order -> replicas stay bit-identical.
 __global__ void rows_mark_kernel(const int32_t* __restrict__ tokens, int T, int32_t* __restrict__ flags) {
+  pdl_grid_sync();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < T) flags[tokens[t]] = 1;
 }
 // rows[0 .. count) = ascending indices r != skip_row with flags[r] != 0 (single block: chunked ballot scan)
 __global__ void __launch_bounds__(1024)
 rows_compact_kernel(const int32_t* __restrict__ flags, int n_rows, int skip_row, int32_t* __restrict__ rows, int32_t* __restrict__ count) {
+  pdl_grid_sync();
   __shared__ int warp_cnt[32];
   __shared__ int base_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -794,6 +810,7 @@ rows_compact_kernel(const int32_t* __restrict__ flags, int n_rows, int skip_row,
 // fp32 [*, 768] rows: gather dst[i] = src[rows[i]], or scatter dst[rows[i]] = src[i]; one warp per row, float4 chunks
 __global__ void rows_move_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ rows, int n,
                                      float* __restrict__ dst, int scatter) {
+  pdl_grid_sync();
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= n) return;
   const int lane = threadIdx.x & 31;
@@ -813,12 +830,12 @@ extern "C" int nbest_rows_touched(nbest_ctx* ctx, const int32_t* tokens, int T, 
     NBEST_CHECK_ARG(ctx, tokens && T >= 0, "null pointer");
     NBEST_CHECK_CUDA(ctx, cudaMemsetAsync(flags, 0, sizeof(int32_t) * (size_t)n_rows, s));
     if (T > 0) {
-      rows_mark_kernel<<<(T + 255) / 256, 256, 0, s>>>(tokens, T, flags);
+      nbest_launch(rows_mark_kernel, dim3((T + 255) / 256), dim3(256), 0, s, tokens, T, flags);
       NBEST_CHECK_LAUNCH(ctx);
     }
   } else {                    // rows / count from the (reduced) flags
     NBEST_CHECK_ARG(ctx, rows && count, "null pointer");
-    rows_compact_kernel<<<1, 1024, 0, s>>>(flags, n_rows, skip_row, rows, count);
+    nbest_launch(rows_compact_kernel, dim3(1), dim3(1024), 0, s, flags, n_rows, skip_row, rows, count);
     NBEST_CHECK_LAUNCH(ctx);
   }
   return NBEST_OK;
@@ -830,7 +847,7 @@ extern "C" int nbest_rows_move_f32(nbest_ctx* ctx, const float* src, const int32
   NBEST_CHECK_ARG(ctx, hidden == H, "hidden must be 768");
   NBEST_CHECK_ARG(ctx, src && rows && dst, "null pointer");
   if (n <= 0) return NBEST_OK;
-  rows_move_f32_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, rows, n, dst, scatter);
+  nbest_launch(rows_move_f32_kernel, dim3((n + 7) / 8), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), src, rows, n, dst, scatter);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
@@ -841,7 +858,7 @@ extern "C" int nbest_rows_gather(nbest_ctx* ctx, const void* src_bf16, const int
   NBEST_CHECK_ARG(ctx, hidden == H, "hidden must be 768");
   NBEST_CHECK_ARG(ctx, src_bf16 && row_idx && dst, "null pointer");
   if (n <= 0) return NBEST_OK;
-  rows_gather_kernel<<<(n + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  nbest_launch(rows_gather_kernel, dim3((n + 7) / 8), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(src_bf16), row_idx, n, dst, dst_is_f32);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
@@ -855,7 +872,7 @@ extern "C" int nbest_rows_scatter(nbest_ctx* ctx, const void* src_bf16, const in
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   NBEST_CHECK_CUDA(ctx, cudaMemsetAsync(dst_bf16, 0, (size_t)T * H * 2, s));
   if (n <= 0) return NBEST_OK;
-  rows_scatter_kernel<<<(n + 7) / 8, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src_bf16), row_idx, n,
+  nbest_launch(rows_scatter_kernel, dim3((n + 7) / 8), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(src_bf16), row_idx, n,
                                                   reinterpret_cast<__nv_bfloat16*>(dst_bf16));
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
@@ -873,7 +890,7 @@ extern "C" int nbest_pack_hyp_ids(nbest_ctx* ctx, const int32_t* tokens, const i
   if (!ctx) return NBEST_EINVAL;
   NBEST_CHECK_ARG(ctx, tokens && cu_seqlens && hyp_id, "null pointer");
   NBEST_CHECK_ARG(ctx, B > 0, "empty batch");
-  pack_hyp_ids_kernel<<<(B + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tokens, cu_seqlens, B, sep_id, hyp_id);
+  nbest_launch(pack_hyp_ids_kernel, dim3((B + 7) / 8), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), tokens, cu_seqlens, B, sep_id, hyp_id);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
@@ -888,7 +905,7 @@ extern "C" int nbest_embed_ln_fwd(nbest_ctx* ctx, const int32_t* tokens, const u
   NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
   NBEST_CHECK_ARG(ctx, p_drop <= 0.f || (int64_t)T * 768 < (1LL << 32), "dropout counter t * 768 + c would wrap 32 bits");
   if (T <= 0) return NBEST_OK;
-  embed_ln_fwd_kernel<<<(T + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  nbest_launch(embed_ln_fwd_kernel, dim3((T + kWarpsPerBlock - 1) / kWarpsPerBlock), dim3(kWarpsPerBlock * 32), 0, reinterpret_cast<cudaStream_t>(stream), 
       tokens, seg, pos, T, word, posemb, type, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y_bf16), mean, rstd,
       drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed);
   NBEST_CHECK_LAUNCH(ctx);
@@ -907,7 +924,7 @@ extern "C" int nbest_embed_ln_bwd(nbest_ctx* ctx, const int32_t* tokens, const u
   if (T <= 0) return NBEST_OK;
   int blocks = (T + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (blocks > ctx->num_sms) blocks = ctx->num_sms;   // one block per SM (register-bound); fewer blocks = fewer column atomics
-  embed_ln_bwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  nbest_launch(embed_ln_bwd_kernel, dim3(blocks), dim3(kWarpsPerBlock * 32), 0, reinterpret_cast<cudaStream_t>(stream), 
       tokens, seg, pos, T, word, posemb, type, gamma, mean, rstd, reinterpret_cast<const __nv_bfloat16*>(dy_bf16),
       drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed, dword, dpos, dtype, dgamma, dbeta, word_pad_row, pos_pad_row);
   NBEST_CHECK_LAUNCH(ctx);
@@ -939,20 +956,20 @@ extern "C" int nbest_ln_fwd_stats(nbest_ctx* ctx, const void* x_bf16, const floa
     int pb = (T + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (pb > 4 * ctx->num_sms) pb = 4 * ctx->num_sms;
     const auto* rp = reinterpret_cast<const float2*>(row_partials);
-    if (depth == 3) ln_fwd_stream_kernel<3><<<pb, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
-    else if (depth == 1) ln_fwd_stream_kernel<1><<<pb, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
-    else ln_fwd_stream_kernel<2><<<pb, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
+    if (depth == 3) nbest_launch(ln_fwd_stream_kernel<3>, dim3(pb), dim3(kWarpsPerBlock * 32), 0, st, xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
+    else if (depth == 1) nbest_launch(ln_fwd_stream_kernel<1>, dim3(pb), dim3(kWarpsPerBlock * 32), 0, st, xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
+    else nbest_launch(ln_fwd_stream_kernel<2>, dim3(pb), dim3(kWarpsPerBlock * 32), 0, st, xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
   } else if (row_partials != nullptr) {
     const auto* rp = reinterpret_cast<const float2*>(row_partials);
-    if (rows == 4) ln_fwd_stats_kernel<4><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
-    else if (rows == 1) ln_fwd_stats_kernel<1><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
-    else ln_fwd_stats_kernel<2><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
+    if (rows == 4) nbest_launch(ln_fwd_stats_kernel<4>, dim3(blocks), dim3(kWarpsPerBlock * 32), 0, st, xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
+    else if (rows == 1) nbest_launch(ln_fwd_stats_kernel<1>, dim3(blocks), dim3(kWarpsPerBlock * 32), 0, st, xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
+    else nbest_launch(ln_fwd_stats_kernel<2>, dim3(blocks), dim3(kWarpsPerBlock * 32), 0, st, xi, gamma, beta, eps, T, rp, n_partials, yo, mean, rstd);
   } else if (rows == 1) {
-    ln_fwd_kernel<1><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, yo, mean, rstd);
+    nbest_launch(ln_fwd_kernel<1>, dim3(blocks), dim3(kWarpsPerBlock * 32), 0, st, xi, gamma, beta, eps, T, yo, mean, rstd);
   } else if (rows == 2) {
-    ln_fwd_kernel<2><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, yo, mean, rstd);
+    nbest_launch(ln_fwd_kernel<2>, dim3(blocks), dim3(kWarpsPerBlock * 32), 0, st, xi, gamma, beta, eps, T, yo, mean, rstd);
   } else {
-    ln_fwd_kernel<4><<<blocks, kWarpsPerBlock * 32, 0, st>>>(xi, gamma, beta, eps, T, yo, mean, rstd);
+    nbest_launch(ln_fwd_kernel<4>, dim3(blocks), dim3(kWarpsPerBlock * 32), 0, st, xi, gamma, beta, eps, T, yo, mean, rstd);
   }
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
@@ -981,7 +998,7 @@ extern "C" int nbest_ln_bwd(nbest_ctx* ctx, const void* dy_bf16, const void* x_b
     NBEST_CHECK_CUDA(ctx, cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnBwdSmem));
     attr = true;
   }
-  ln_bwd_kernel<<<blocks, kWarpsPerBlock * 32, kLnBwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  nbest_launch(ln_bwd_kernel, dim3(blocks), dim3(kWarpsPerBlock * 32), kLnBwdSmem, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16), mean, rstd, gamma, T,
       reinterpret_cast<__nv_bfloat16*>(dx_bf16), p_drop > 0.f ? reinterpret_cast<__nv_bfloat16*>(dx_masked_bf16) : nullptr,
       drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed, dgamma, dbeta, dbias);
@@ -1000,7 +1017,7 @@ extern "C" int nbest_colsum_bf16(nbest_ctx* ctx, const void* x_bf16, int T, int 
   int rows_per_block = (T + gy - 1) / gy;
   if (rows_per_block < 32) rows_per_block = 32;
   gy = (T + rows_per_block - 1) / rows_per_block;
-  colsum_kernel<<<dim3(gx, gy), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  nbest_launch(colsum_kernel, dim3(dim3(gx, gy)), dim3(threads), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(x_bf16), T, N, rows_per_block, out);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
@@ -1015,7 +1032,7 @@ extern "C" int nbest_cast_f32_bf16(nbest_ctx* ctx, const float* src, void* dst_b
   int64_t blocks = (n / 8 + 255) / 256;
   if (blocks > 8 * ctx->num_sms) blocks = 8 * ctx->num_sms;
   if (blocks < 1) blocks = 1;
-  cast_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), n);
+  nbest_launch(cast_kernel, dim3((int)blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), n);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }

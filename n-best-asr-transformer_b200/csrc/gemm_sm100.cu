@@ -140,6 +140,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();   // everything above (barriers, TMEM, descriptor prefetch) ran under the previous kernel's tail
 
   // ---- work distribution. Static: unit u takes items u, u + num_units, ... Dynamic (g.sched != NULL): the leader's
   // producer thread draws items from a global counter and publishes them through a small shared-memory ring to the other
@@ -528,18 +529,19 @@ int launch(nbest_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const
   static int max_units_dev[64] = {};  // per instantiation and device: CTAs (CG = 1) or co-resident CTA pairs (CG = 2)
   int& max_units = max_units_dev[ctx->device & 63];
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = C_::kSmemBytes;
   cfg.stream = stream;
+  cfg.attrs = attr;
   if (CG == 2) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    attr[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
+    attr[cfg.numAttrs].val.clusterDim.x = 2;
+    attr[cfg.numAttrs].val.clusterDim.y = 1;
+    attr[cfg.numAttrs].val.clusterDim.z = 1;
+    ++cfg.numAttrs;
   }
+  const int n_cluster_attrs = cfg.numAttrs;
   if (max_units == 0) {
     NBEST_CHECK_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::kSmemBytes));
     if (CG == 2) {
@@ -560,6 +562,12 @@ int launch(nbest_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const
   if (avail < 1) avail = 1;
   const int units = num_work < avail ? num_work : avail;
   cfg.gridDim = dim3(units * CG);
+  cfg.numAttrs = n_cluster_attrs;
+  if (g_nbest_pdl) {
+    attr[cfg.numAttrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
+    ++cfg.numAttrs;
+  }
   NBEST_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, tmC, tmC2, g));
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;

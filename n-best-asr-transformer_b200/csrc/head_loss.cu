@@ -38,6 +38,7 @@ stc_head_fwd_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restri
                     const float* __restrict__ bias, Hier h, const uint8_t* __restrict__ none_col, uint32_t thr, float rscale,
                     uint32_t seed, float* __restrict__ cls, float* __restrict__ logits, float* __restrict__ top_scores,
                     float* __restrict__ bottom_scores, float* __restrict__ final_scores, uint8_t* __restrict__ decode) {
+  pdl_grid_sync();
   __shared__ float f[H];
   __shared__ float z[kMaxCols];
   __shared__ float sc[kMaxCols];   // sigmoid / softmax of z
@@ -176,6 +177,7 @@ __device__ __forceinline__ void recompute_scores(const Hier& h, const float* z, 
 __global__ void __launch_bounds__(256)
 stc_loss_kernel(const float* __restrict__ logits, const float* __restrict__ labels, int B, Hier h,
                 float* __restrict__ losses, float* __restrict__ dlogits) {
+  pdl_grid_sync();
   __shared__ float z[kMaxCols], sc[kMaxCols], ds[kMaxCols], dq[kMaxCols], dfin[kMaxCols];
   __shared__ float y[kMaxBottom];
   __shared__ float red[3];
@@ -253,6 +255,7 @@ stc_loss_kernel(const float* __restrict__ logits, const float* __restrict__ labe
 
 __global__ void mse_kernel(const float* __restrict__ a, const float* __restrict__ t, int64_t n, float coef /*scale/n*/,
                            float* __restrict__ losses, float* __restrict__ da, float* __restrict__ dt) {
+  pdl_grid_sync();
   float acc = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float d = a[i] - t[i];
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(256)
 stc_scores_bwd_kernel(const float* __restrict__ top_scores, const float* __restrict__ bottom_scores,
                       const float* __restrict__ d_top, const float* __restrict__ d_bottom, const float* __restrict__ d_final,
                       int B, Hier h, float* __restrict__ dlogits) {
+  pdl_grid_sync();
   __shared__ float sc[kMaxCols], ds[kMaxCols], dq[kMaxCols], dfin[kMaxCols];
   const int b = blockIdx.x;
   const int nb = h.n_cols - h.n_top;
@@ -304,6 +308,7 @@ constexpr int kWgradSplits = 8;
 __global__ void __launch_bounds__(192)
 stc_head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ cls, int B, Hier h, uint32_t thr,
                       float rscale, uint32_t seed, float* __restrict__ dW, float* __restrict__ dbias) {
+  pdl_grid_sync();
   const int c = blockIdx.x;
   const int g = h.col_group[c];
   const int per = (B + kWgradSplits - 1) / kWgradSplits;
@@ -344,6 +349,7 @@ stc_head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict
 __global__ void __launch_bounds__(192)
 stc_head_dgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ W, int B, Hier h, uint32_t thr,
                       float rscale, uint32_t seed, float* __restrict__ dcls, int accumulate) {
+  pdl_grid_sync();
   __shared__ float dl[kMaxCols];
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < h.n_cols; c += blockDim.x) dl[c] = dlogits[(int64_t)b * h.n_cols + c];
@@ -385,6 +391,7 @@ stc_head_dgrad_kernel(const float* __restrict__ dlogits, const float* __restrict
 
 __global__ void cls_scatter_kernel(const float* __restrict__ dcls, const int32_t* __restrict__ cu,
                                    __nv_bfloat16* __restrict__ dx) {
+  pdl_grid_sync();
   const int b = blockIdx.x;
   __nv_bfloat16* row = dx + (int64_t)cu[b] * H;
   for (int d = threadIdx.x; d < H; d += blockDim.x) row[d] = __float2bfloat16_rn(dcls[(int64_t)b * H + d]);
@@ -394,6 +401,7 @@ __global__ void cls_scatter_kernel(const float* __restrict__ dcls, const int32_t
 __global__ void __launch_bounds__(256)
 stc_metrics_kernel(const uint8_t* __restrict__ decode, const float* __restrict__ labels, const uint8_t* __restrict__ col_mask,
                    int B, int nb, unsigned long long* __restrict__ counters) {
+  pdl_grid_sync();
   __shared__ unsigned int part[4];
   if (threadIdx.x < 4) part[threadIdx.x] = 0;
   __syncthreads();
@@ -461,7 +469,7 @@ extern "C" int nbest_stc_head_fwd(nbest_ctx* ctx, const void* x_bf16, const int3
                   "null pointer");
   NBEST_CHECK_ARG(ctx, B > 0, "empty batch");
   NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
-  stc_head_fwd_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  nbest_launch(stc_head_fwd_kernel, dim3(B), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(x_bf16), cu_seqlens, B, W, bias, h, none_col_mask, drop_threshold(p_drop),
       1.0f / (1.0f - p_drop), seed, cls, logits, top_scores, bottom_scores, final_scores, decode);
   NBEST_CHECK_LAUNCH(ctx);
@@ -479,13 +487,13 @@ extern "C" int nbest_stc_loss_fwd_bwd(nbest_ctx* ctx, const float* logits, const
   NBEST_CHECK_ARG(ctx, logits && labels && losses && dlogits, "null pointer");
   NBEST_CHECK_ARG(ctx, B > 0, "empty batch");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  stc_loss_kernel<<<B, 256, 0, s>>>(logits, labels, B, h, losses, dlogits);
+  nbest_launch(stc_loss_kernel, dim3(B), dim3(256), 0, s, logits, labels, B, h, losses, dlogits);
   NBEST_CHECK_LAUNCH(ctx);
   if (asr_cls && trans_cls) {
     const int64_t n = (int64_t)B * hidden;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 256) blocks = 256;
-    mse_kernel<<<blocks, 256, 0, s>>>(asr_cls, trans_cls, n, mse_scale / (float)n, losses, d_asr_cls, d_trans_cls);
+    nbest_launch(mse_kernel, dim3(blocks), dim3(256), 0, s, asr_cls, trans_cls, n, mse_scale / (float)n, losses, d_asr_cls, d_trans_cls);
     NBEST_CHECK_LAUNCH(ctx);
   }
   return NBEST_OK;
@@ -500,7 +508,7 @@ extern "C" int nbest_stc_scores_bwd(nbest_ctx* ctx, const float* top_scores, con
   if (rc) return rc;
   NBEST_CHECK_ARG(ctx, top_scores && bottom_scores && dlogits, "null pointer");
   NBEST_CHECK_ARG(ctx, B > 0, "empty batch");
-  stc_scores_bwd_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(top_scores, bottom_scores, d_top, d_bottom,
+  nbest_launch(stc_scores_bwd_kernel, dim3(B), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), top_scores, bottom_scores, d_top, d_bottom,
                                                                                 d_final, B, h, dlogits);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
@@ -519,10 +527,10 @@ extern "C" int nbest_stc_head_bwd(nbest_ctx* ctx, const float* dlogits, const fl
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const uint32_t thr = drop_threshold(p_drop);
   const float rscale = 1.0f / (1.0f - p_drop);
-  stc_head_wgrad_kernel<<<dim3(h.n_cols, kWgradSplits), 192, 0, s>>>(dlogits, cls, B, h, thr, rscale, seed, dW, dbias);
+  nbest_launch(stc_head_wgrad_kernel, dim3(dim3(h.n_cols, kWgradSplits)), dim3(192), 0, s, dlogits, cls, B, h, thr, rscale, seed, dW, dbias);
   NBEST_CHECK_LAUNCH(ctx);
   NBEST_CHECK_ARG(ctx, h.n_groups + 1 <= 16, "at most 15 multi-way value groups (4 keep bits per group in one word)");
-  stc_head_dgrad_kernel<<<B, 192, 0, s>>>(dlogits, W, B, h, thr, rscale, seed, dcls, accumulate_dcls);
+  nbest_launch(stc_head_dgrad_kernel, dim3(B), dim3(192), 0, s, dlogits, W, B, h, thr, rscale, seed, dcls, accumulate_dcls);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
@@ -533,7 +541,7 @@ extern "C" int nbest_stc_metrics(nbest_ctx* ctx, const uint8_t* decode, const fl
   NBEST_CHECK_ARG(ctx, decode && labels && counters, "null pointer");
   NBEST_CHECK_ARG(ctx, B >= 0 && n_bottom > 0, "bad shape");
   if (B == 0) return NBEST_OK;
-  stc_metrics_kernel<<<(B + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  nbest_launch(stc_metrics_kernel, dim3((B + 7) / 8), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       decode, labels, col_mask, B, n_bottom, reinterpret_cast<unsigned long long*>(counters));
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
@@ -546,7 +554,7 @@ extern "C" int nbest_cls_scatter(nbest_ctx* ctx, const float* dcls, const int32_
   NBEST_CHECK_ARG(ctx, dcls && cu_seqlens && dx_bf16, "null pointer");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   NBEST_CHECK_CUDA(ctx, cudaMemsetAsync(dx_bf16, 0, (size_t)T * H * 2, s));
-  cls_scatter_kernel<<<B, 256, 0, s>>>(dcls, cu_seqlens, reinterpret_cast<__nv_bfloat16*>(dx_bf16));
+  nbest_launch(cls_scatter_kernel, dim3(B), dim3(256), 0, s, dcls, cu_seqlens, reinterpret_cast<__nv_bfloat16*>(dx_bf16));
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }

@@ -14,6 +14,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization (common.h nbest_launch): its CTAs may
+// become resident while the previous kernel of the stream is still draining, run their prologue, and block here until
+// that kernel has completed and its memory is visible. Right behind the wait the kernel releases ITS dependent, so at most
+// one successor is ever staged. Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
