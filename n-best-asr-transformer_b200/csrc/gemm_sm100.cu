@@ -394,18 +394,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
               }
               if constexpr (EPI == NBEST_EPI_BIAS_GELU) {
+                // packed fp32x2 evaluation: two elements per FFMA2 / FMUL2 (ptx.cuh gelu_fwd_grad2)
                 if (both) {
 #pragma unroll
                   for (int s4 = 0; s4 < 4; ++s4) {
                     float d[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) gelu_fwd_grad(v[8 * s4 + j], v[8 * s4 + j], d[j]);
+                    for (int j = 0; j < 8; j += 2) {
+                      f32x2 gg, dd;
+                      gelu_fwd_grad2(f2_pack(v[8 * s4 + j], v[8 * s4 + j + 1]), gg, dd);
+                      f2_unpack(gg, v[8 * s4 + j], v[8 * s4 + j + 1]);
+                      f2_unpack(dd, d[j], d[j + 1]);
+                    }
                     *reinterpret_cast<uint4*>(st + 4096 + unit_off(lane, cc * 4 + s4)) =
                         make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
                   }
                 } else {
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) v[j] = gelu_fwd(v[j]);
+                  for (int j = 0; j < 32; j += 2) f2_unpack(gelu_fwd2(f2_pack(v[j], v[j + 1])), v[j], v[j + 1]);
                 }
               } else if constexpr (EPI == NBEST_EPI_BIAS_DROP_RES) {
                 if (g.drop_thresh != 0) {

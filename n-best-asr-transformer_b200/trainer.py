@@ -125,7 +125,9 @@ class DataParallelTrainer:
         # pairs wait for (measured: dgrad GEMMs 22 % slower under overlap). One layer per bucket (28 MB) fits a window.
         env_slots = os.environ.get("NBEST_COMM_SLOTS")
         self.comm_slots = self.world > 1 and (env_slots is None or env_slots != "0")
-        segments = model_segments(model, 1 if (self.comm_slots and "NBEST_BUCKET_LAYERS" not in os.environ) else None)
+        # (bucket size re-measured in round 2 with PDL + dynamic GEMM scheduling, N = 2: one layer per bucket at the slots
+        #  10.89 ms, two layers 10.58 ms, immediate launch 10.64 - 10.74 ms)
+        segments = model_segments(model, None)
         self.bucketer = GradBucketer(model.flat.grads, segments, group, self.comm_stream)
         self.group = group
         self._pending = []
