@@ -82,7 +82,9 @@ def model_segments(model, layers_per_bucket=None):
     lay = lambda l: "bert_encoder.encoder.layer.%d.attention.self.query.weight" % l
     segs, hi, end = [], L, f.total
     while hi > 0:
-        lo = max(0, hi - layers_per_bucket)
+        # the lowest layers go one per bucket: whatever is still un-reduced when the backward ends is the exposed tail of
+        # the step (nothing is left to overlap with), so the last bucket before the embeddings is kept small
+        lo = max(0, hi - (layers_per_bucket if hi > layers_per_bucket else 1))
         segs.append(("layer%d" % lo, start(lay(lo)), end))
         end, hi = start(lay(lo)), lo
     segs.append(("emb", 0, end))
