@@ -385,12 +385,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if constexpr (kHasBias) {
                 const float* bsrc = bias_s + c * 32;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
+                for (int j = 0; j < 32; j += 4) {     // packed fp32x2 adds (two elements per FADD2)
                   const float4 b = *reinterpret_cast<const float4*>(bsrc + j);
-                  v[j] += b.x;
-                  v[j + 1] += b.y;
-                  v[j + 2] += b.z;
-                  v[j + 3] += b.w;
+                  f2_unpack(f2_add(f2_pack(v[j], v[j + 1]), f2_pack(b.x, b.y)), v[j], v[j + 1]);
+                  f2_unpack(f2_add(f2_pack(v[j + 2], v[j + 3]), f2_pack(b.z, b.w)), v[j + 2], v[j + 3]);
                 }
               }
               if constexpr (EPI == NBEST_EPI_BIAS_GELU) {
@@ -420,42 +418,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   for (int j = 0; j < 32; j += 4) {
                     bool k0, k1, k2, k3;
                     dropout_keep4(g.seed, base + j, g.drop_thresh, k0, k1, k2, k3);   // base % 4 == 0 (N, nc multiples of 32)
-                    v[j] = k0 ? v[j] * g.drop_scale : 0.f;
-                    v[j + 1] = k1 ? v[j + 1] * g.drop_scale : 0.f;
-                    v[j + 2] = k2 ? v[j + 2] * g.drop_scale : 0.f;
-                    v[j + 3] = k3 ? v[j + 3] * g.drop_scale : 0.f;
+                    f2_unpack(f2_mul(f2_pack(v[j], v[j + 1]), f2_pack(k0 ? g.drop_scale : 0.f, k1 ? g.drop_scale : 0.f)), v[j], v[j + 1]);
+                    f2_unpack(f2_mul(f2_pack(v[j + 2], v[j + 3]), f2_pack(k2 ? g.drop_scale : 0.f, k3 ? g.drop_scale : 0.f)), v[j + 2],
+                              v[j + 3]);
                   }
                 }
+                f32x2 rs2 = 0ull, rq2 = 0ull;      // (0.f, 0.f)
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                  v[2 * j] += bf16lo(auxrow[j]);
-                  v[2 * j + 1] += bf16hi(auxrow[j]);
+                  const f32x2 x2 = f2_add(f2_pack(v[2 * j], v[2 * j + 1]), f2_pack(bf16lo(auxrow[j]), bf16hi(auxrow[j])));
+                  f2_unpack(x2, v[2 * j], v[2 * j + 1]);
+                  rs2 = f2_add(rs2, x2);           // partial LayerNorm statistics of the row the next kernel normalises
+                  rq2 = f2_fma(x2, x2, rq2);
                 }
-                if (g.out2 != nullptr) {       // partial LayerNorm statistics of the row the next kernel normalises
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) {
-                    rsum += v[j];
-                    rsq = fmaf(v[j], v[j], rsq);
-                  }
+                if (g.out2 != nullptr) {
+                  float a0, a1, q0, q1;
+                  f2_unpack(rs2, a0, a1);
+                  f2_unpack(rq2, q0, q1);
+                  rsum += a0 + a1;
+                  rsq += q0 + q1;
                 }
               } else if constexpr (EPI == NBEST_EPI_DGELU) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {   // aux = gelu'(u), saved by the forward's NBEST_EPI_BIAS_GELU epilogue
-                  v[2 * j] *= bf16lo(auxrow[j]);
-                  v[2 * j + 1] *= bf16hi(auxrow[j]);
-                }
+                for (int j = 0; j < 16; ++j)     // aux = gelu'(u), saved by the forward's NBEST_EPI_BIAS_GELU epilogue
+                  f2_unpack(f2_mul(f2_pack(v[2 * j], v[2 * j + 1]), f2_pack(bf16lo(auxrow[j]), bf16hi(auxrow[j]))), v[2 * j], v[2 * j + 1]);
               } else if constexpr (EPI == NBEST_EPI_ADD) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  v[2 * j] += bf16lo(auxrow[j]);
-                  v[2 * j + 1] += bf16hi(auxrow[j]);
-                }
+                for (int j = 0; j < 16; ++j)
+                  f2_unpack(f2_add(f2_pack(v[2 * j], v[2 * j + 1]), f2_pack(bf16lo(auxrow[j]), bf16hi(auxrow[j]))), v[2 * j], v[2 * j + 1]);
               } else if constexpr (EPI == NBEST_EPI_DELTA) {
+                f32x2 ds2 = 0ull;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  dsum = fmaf(v[2 * j], bf16lo(auxrow[j]), dsum);
-                  dsum = fmaf(v[2 * j + 1], bf16hi(auxrow[j]), dsum);
-                }
+                for (int j = 0; j < 16; ++j)
+                  ds2 = f2_fma(f2_pack(v[2 * j], v[2 * j + 1]), f2_pack(bf16lo(auxrow[j]), bf16hi(auxrow[j])), ds2);
+                float e0, e1;
+                f2_unpack(ds2, e0, e1);
+                dsum += e0 + e1;
               }
 #pragma unroll
               for (int s4 = 0; s4 < 4; ++s4)
