@@ -237,6 +237,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-dropout", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the training step as a CUDA graph (nbest_b200.graph; one GPU, BERT packing, training). auto: "
+                         "time both the eager and the graphed step and report the faster one, naming it in config.step_mode")
+    ap.add_argument("--bucket", default="3,256", help="shape buckets of the graphed step: fillers per stream, token multiple")
     ap.add_argument("--skip-transcript", action="store_true",
                     help="do not run the transcript stream at all (without --add_l2_loss the reference computes it forward-only "
                          "and never uses the result; default = run it, as the reference does)")
@@ -338,6 +342,35 @@ def main():
             losses = trainer.step(d["ids"], d["labels"], d["trans_ids"], d["seg"], d["trans_seg"], h["lens"], h["trans_lens"])
         return losses.cpu()                                         # D2H read of the step's loss terms (synchronises)
 
+    # ---- graphed step (one GPU): the same batches with filler sequences appended by the data pipeline ahead of the timed
+    # region (like collation / pinning), so that token counts fall on shape buckets and every batch replays a captured graph
+    use_graph = args.graph != "off" and world == 1 and args.model == "bert" and not infer
+    gt = None
+    if use_graph:
+        from nbest_b200.graph import GraphedTrainer, add_fillers
+        n_fill, mult = (int(x) for x in args.bucket.split(","))
+        gt = GraphedTrainer(trainer)
+        hostg, devg = [], []
+        for h in host:
+            ids, seg, lens = add_fillers(h["ids"], h["seg"], h["lens"], n_fill, mult, args.max_len)
+            g = dict(ids=ids, seg=seg, lens=lens, labels=h["labels"], trans_ids=None, trans_seg=None, trans_lens=None)
+            if not skip_t:
+                g["trans_ids"], g["trans_seg"], g["trans_lens"] = add_fillers(h["trans_ids"], h["trans_seg"], h["trans_lens"],
+                                                                              n_fill, mult, args.max_len)
+            hostg.append({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in g.items()})
+            devg.append({k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in g.items()})
+        h2d_bytes_graph = int(np.mean([sum(h[k].numel() * h[k].element_size() for k in keys if h[k] is not None) for h in hostg]))
+
+    def step_graph_dev(i):
+        b = devg[i % NB]
+        return gt.step(b["ids"], b["labels"], b["trans_ids"], b["seg"], b["trans_seg"], b["lens"], b["trans_lens"], n_real=args.batch)
+
+    def step_graph_host(i):
+        h = hostg[i % NB]       # pinned host tensors: the copies into the graph's static inputs are the step's H2D traffic
+        losses = gt.step(h["ids"], h["labels"], h["trans_ids"], h["seg"], h["trans_seg"], h["lens"], h["trans_lens"],
+                         n_real=args.batch)
+        return losses.cpu()                                         # D2H read of the step's loss terms (synchronises)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -366,10 +399,29 @@ def main():
         step_dev(i)
     sampler = ClockSampler(local) if rank == 0 else None
     ms, launches, last = timed(step_dev, args.steps)
-    clocks = sampler.stop() if sampler else None
     for i in range(2):
         step_host(i)
     ms_e2e, _, last_losses = timed(step_host, args.steps)
+    modes = dict(eager=dict(ms_per_step=ms / args.steps, e2e_ms_per_step=ms_e2e / args.steps, gpu_launches=int(launches)))
+    step_mode = "eager (one Python-issued launch per kernel)"
+    if gt is not None:
+        for i in range(NB + 1 + args.warmup):                        # first call eager, then one capture per batch shape
+            step_graph_dev(i)
+        k0 = gt.kernels_total
+        ms_g, _, _ = timed(step_graph_dev, args.steps)
+        launches_g = gt.kernels_total - k0
+        for i in range(2):
+            step_graph_host(i)
+        ms_e2e_g, _, last_g = timed(step_graph_host, args.steps)
+        modes["graph"] = dict(ms_per_step=ms_g / args.steps, e2e_ms_per_step=ms_e2e_g / args.steps, gpu_launches=int(launches_g),
+                              graphs_captured=gt.captures, replays=gt.replays, eager_fallbacks=gt.eager_steps - 1,
+                              capture_error=gt.capture_error, h2d_bytes_per_step=h2d_bytes_graph,
+                              shape_buckets="%d filler sequences per stream, token counts rounded up to multiples of %d "
+                                            "(appended by the data pipeline ahead of the timed region)" % (n_fill, mult))
+        if gt.captures > 0 and gt.capture_error is None and (args.graph == "on" or ms_e2e_g < ms_e2e):
+            ms, ms_e2e, launches, last_losses, h2d_bytes = ms_g, ms_e2e_g, launches_g, last_g, h2d_bytes_graph
+            step_mode = "cuda-graph replay of the whole step (nbest_b200.graph.GraphedTrainer)"
+    clocks = sampler.stop() if sampler else None
     if not infer and not bool(torch.isfinite(last_losses).all()):
         raise SystemExit("non-finite loss in the benchmark step")
     d2h_bytes = int(dec_host.numel()) if infer else 16
@@ -426,6 +478,7 @@ def main():
                 dropout="off" if (args.no_dropout or infer) else "0.1/0.1/0.3",
                 streams="asr forward + decode (eval mode)" if infer else "asr fwd+bwd, transcript %s" % (
                     "fwd+bwd" if args.l2 else ("skipped (--skip-transcript)" if skip_t else "fwd only (as the reference)")),
+                step_mode=step_mode,
                 l2_flush="per-step working set (activations + fp32 weights%s, > 1 GB) exceeds the 126 MB L2" % (
                     "" if infer else " + Adam state")),
             clocks=clocks,
@@ -437,6 +490,7 @@ def main():
                                                      args.model == "bert") else None,
                           peak_source=pk["src"] + " bf16_tflops_sustained", gemm_ms_per_step=gemm_ms,
                           gemm_share_of_step=gemm_ms / (step_s * 1e3)),
+            modes=modes,
             tc_util=dict(asr_stream_formula=alg / (step_s * pk["tf_sustained"] * 1e12),
                          all_executed_streams=alg_all / (step_s * pk["tf_sustained"] * 1e12)),
             kernels=kernels)

@@ -10,7 +10,8 @@
  * Conventions
  *   - plain C: pointers and sizes only, no torch / C++ types.
  *   - every data pointer is a DEVICE pointer owned by the caller; the library never allocates or frees device
- *     memory (one exception: a 512-byte scheduler buffer owned by the context, see nbest_ctx_set_gemm_dynamic). `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it, no internal sync.
+ *     memory (one exception: a 536-byte buffer owned by the context — the GEMM scheduler ring, see
+ *     nbest_ctx_set_gemm_dynamic, and the per-step state record, see nbest_ctx_set_step_state). `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it, no internal sync.
  *   - "bf16" buffers are raw uint16 bfloat16, row-major; "f32" are float.
  *   - return value: NBEST_OK (0) or a negative nbest_status; nbest_last_error(ctx) gives the message.
  *   - one nbest_ctx per process / GPU rank; calls on one ctx must come from one thread at a time.
@@ -24,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NBEST_ABI_VERSION 2
+#define NBEST_ABI_VERSION 3
 
 typedef struct nbest_ctx nbest_ctx;
 
@@ -53,6 +54,20 @@ int nbest_ctx_set_sm_reserve(nbest_ctx* ctx, int n_sms);
  * on one GPU, where nothing competes for SMs — hence off there — and dgrad GEMMs 6 % faster under NCCL overlap). Needs the context's 512-byte device scheduler buffer — the only device memory the
  * library allocates itself (nbest_ctx_create / nbest_ctx_destroy). */
 int nbest_ctx_set_gemm_dynamic(nbest_ctx* ctx, int on);
+/* Per-step state for CUDA-graph replay of the training step (replaces nothing in the reference, whose step is ~3,300
+ * eager launches, n_best_asr_bert.py:254-277). A captured graph bakes every by-value argument in — the dropout seeds and
+ * the optimizer's schedule multiplier among them — so what must change from one replay to the next is read from a
+ * 24-byte device record owned by the context:
+ *   salt         XORed into the (host-mixed) seed of EVERY kernel that draws dropout masks (embedding, GEMM dropout
+ *                epilogue, LayerNorm backward, the attention kernels, the classifier head). 0 — the state after
+ *                nbest_ctx_create — leaves the by-value seeds as they are.
+ *   sched, inv_bc1, inv_sqrt_bc2   BertAdam's / AdamW's schedule multiplier (models/optimization.py:289-293) and
+ *                torch.optim.Adam's bias corrections of THIS step; read by nbest_adam_step / nbest_bertadam_step in place
+ *                of their by-value arguments while nbest_ctx_set_step_indirect(ctx, 1) is in force.
+ * nbest_ctx_set_step_state enqueues a one-thread kernel on `stream` that writes the record: call it ahead of the graph
+ * launch (stream order makes it visible to the replayed kernels, which read it after their grid dependency wait). */
+int nbest_ctx_set_step_state(nbest_ctx* ctx, uint32_t salt, double sched, float inv_bc1, float inv_sqrt_bc2, void* stream);
+int nbest_ctx_set_step_indirect(nbest_ctx* ctx, int on);
 /* TMA descriptor cache hits so far (host-overhead diagnostics). */
 uint64_t nbest_tmap_cache_hits(nbest_ctx* ctx);
 

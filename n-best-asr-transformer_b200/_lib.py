@@ -35,6 +35,8 @@ _SIGNATURES = {
     "nbest_ctx_set_sm_reserve": (C.c_int, [_vp, C.c_int]),
     "nbest_tmap_cache_hits": (_u64, [_vp]),
     "nbest_ctx_set_gemm_dynamic": (C.c_int, [_vp, C.c_int]),
+    "nbest_ctx_set_step_state": (C.c_int, [_vp, _u32, _f64, _f32, _f32, _vp]),
+    "nbest_ctx_set_step_indirect": (C.c_int, [_vp, C.c_int]),
     "nbest_pack_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nbest_pack_hyp_ids": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "nbest_pack_batch_dual": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp,
@@ -147,6 +149,14 @@ class Context:
 
     def set_gemm_dynamic(self, on):
         self.check(self._l.nbest_ctx_set_gemm_dynamic(self.handle, int(bool(on))))
+
+    def set_step_state(self, salt, sched=1.0, inv_bc1=1.0, inv_sqrt_bc2=1.0, stream=None):
+        """Per-step scalars a replayed CUDA graph of the training step reads from device memory (include/nbest_sm100.h)."""
+        self.check(self._l.nbest_ctx_set_step_state(self.handle, int(salt) & 0xFFFFFFFF, float(sched), float(inv_bc1),
+                                                    float(inv_sqrt_bc2), stream))
+
+    def set_step_indirect(self, on):
+        self.check(self._l.nbest_ctx_set_step_indirect(self.handle, int(bool(on))))
 
     def tmap_cache_hits(self):
         return int(self._l.nbest_tmap_cache_hits(self.handle))

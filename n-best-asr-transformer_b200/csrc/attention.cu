@@ -126,8 +126,9 @@ template <int HPC>
 __global__ void __launch_bounds__(kThreads, 4)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu, const uint8_t* __restrict__ key_valid,
                 int heads, int T, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, float scale, uint32_t thr,
-                float rscale, uint32_t seed, int min_len) {
+                float rscale, uint32_t seed, const uint32_t* __restrict__ salt, int min_len) {
   pdl_grid_sync();
+  seed ^= step_salt(salt);
   const int qb = blockIdx.x, h0 = blockIdx.y * HPC, b = blockIdx.z;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   const int q0 = qb * BLK;
@@ -293,8 +294,9 @@ __global__ void __launch_bounds__(kThreads, 3)
 attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
                      const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
                      const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                     float scale, uint32_t thr, float rscale, uint32_t seed, int dpitch, int min_len) {
+                     float scale, uint32_t thr, float rscale, uint32_t seed, const uint32_t* __restrict__ salt, int dpitch, int min_len) {
   pdl_grid_sync();
+  seed ^= step_salt(salt);
   const int kb = blockIdx.x, h0 = blockIdx.y * HPC, b = blockIdx.z;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   const int k0 = kb * BLK;
@@ -416,8 +418,9 @@ __global__ void __launch_bounds__(kThreads, 3)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
                    const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                   float scale, uint32_t thr, float rscale, uint32_t seed, int dpitch, int min_len) {
+                   float scale, uint32_t thr, float rscale, uint32_t seed, const uint32_t* __restrict__ salt, int dpitch, int min_len) {
   pdl_grid_sync();
+  seed ^= step_salt(salt);
   const int qb = blockIdx.x, h0 = blockIdx.y * HPC, b = blockIdx.z;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   const int q0 = qb * BLK;
@@ -544,8 +547,9 @@ __global__ void __launch_bounds__(kThreads, 2)
 attn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
                       const uint8_t* __restrict__ key_valid, int heads, int T, const __nv_bfloat16* __restrict__ dout,
                       const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                      float scale, uint32_t thr, float rscale, uint32_t seed, int dpitch) {
+                      float scale, uint32_t thr, float rscale, uint32_t seed, const uint32_t* __restrict__ salt, int dpitch) {
   pdl_grid_sync();
+  seed ^= step_salt(salt);
   const int h0 = blockIdx.x * HPC, b = blockIdx.y;
   const int s0 = cu[b], L = cu[b + 1] - s0;
   if (L <= 0 || L > BLK) return;               // longer sequences: attn_bwd_dkdv_kernel + attn_bwd_dq_kernel
@@ -741,10 +745,10 @@ extern "C" int nbest_attn_varlen_fwd2(nbest_ctx* ctx, const void* qkv_bf16, cons
   }
   if (heads % 4 == 0)
     nbest_launch(attn_fwd_kernel<4>, dim3(dim3(nqb, heads / 4, B)), dim3(kThreads), sizeof(FwdSmem), s, q, cu_seqlens, key_valid, heads, T, o, lse,
-                                                                              0.125f, thr, rscale, seed, min_len);
+                                                                              0.125f, thr, rscale, seed, nbest_salt(ctx), min_len);
   else
     nbest_launch(attn_fwd_kernel<1>, dim3(dim3(nqb, heads, B)), dim3(kThreads), sizeof(FwdSmem), s, q, cu_seqlens, key_valid, heads, T, o, lse, 0.125f,
-                                                                          thr, rscale, seed, min_len);
+                                                                          thr, rscale, seed, nbest_salt(ctx), min_len);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
@@ -811,7 +815,7 @@ extern "C" int nbest_attn_varlen_bwd2(nbest_ctx* ctx, const void* qkv_bf16, cons
       fattr_dev[ctx->device & 63] = true;
     }
     nbest_launch(attn_bwd_fused_kernel<4>, dim3(dim3(heads / 4, B)), dim3(kThreads), sizeof(FusedSmem), s, q, cu_seqlens, key_valid, heads, T, g, lse,
-                                                                                   delta_ws, dq, 0.125f, thr, rscale, seed, dpitch);
+                                                                                   delta_ws, dq, 0.125f, thr, rscale, seed, nbest_salt(ctx), dpitch);
     NBEST_CHECK_LAUNCH(ctx);
     if (max_len <= BLK) return NBEST_OK;
     min_len = BLK + 1;
@@ -821,18 +825,18 @@ extern "C" int nbest_attn_varlen_bwd2(nbest_ctx* ctx, const void* qkv_bf16, cons
   if (heads % 4 == 0 && !use_fused) {
     const dim3 grid(nb, heads / 4, B);
     nbest_launch(attn_bwd_dkdv_kernel<4>, dim3(grid), dim3(kThreads), sizeof(DkdvSmem), s, q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq,
-                                                                    0.125f, thr, rscale, seed, dpitch, min_len);
+                                                                    0.125f, thr, rscale, seed, nbest_salt(ctx), dpitch, min_len);
     NBEST_CHECK_LAUNCH(ctx);
     nbest_launch(attn_bwd_dq_kernel<4>, dim3(grid), dim3(kThreads), sizeof(DqSmem), s, q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f,
-                                                                thr, rscale, seed, dpitch, min_len);
+                                                                thr, rscale, seed, nbest_salt(ctx), dpitch, min_len);
     NBEST_CHECK_LAUNCH(ctx);
   } else {
     const dim3 grid(nb, heads, B);
     nbest_launch(attn_bwd_dkdv_kernel<1>, dim3(grid), dim3(kThreads), sizeof(DkdvSmem), s, q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq,
-                                                                    0.125f, thr, rscale, seed, dpitch, min_len);
+                                                                    0.125f, thr, rscale, seed, nbest_salt(ctx), dpitch, min_len);
     NBEST_CHECK_LAUNCH(ctx);
     nbest_launch(attn_bwd_dq_kernel<1>, dim3(grid), dim3(kThreads), sizeof(DqSmem), s, q, cu_seqlens, key_valid, heads, T, g, lse, delta_ws, dq, 0.125f,
-                                                                thr, rscale, seed, dpitch, min_len);
+                                                                thr, rscale, seed, nbest_salt(ctx), dpitch, min_len);
     NBEST_CHECK_LAUNCH(ctx);
   }
   return NBEST_OK;

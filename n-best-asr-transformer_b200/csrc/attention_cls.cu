@@ -56,8 +56,9 @@ __device__ __forceinline__ float dot_row64(const __nv_bfloat16* p, const float (
 __global__ void __launch_bounds__(kWarps * 32)
 attn_cls_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu, const uint8_t* __restrict__ key_valid,
                     int B, int heads, int T, __nv_bfloat16* __restrict__ out_cls, float* __restrict__ lse_cls, float scale,
-                    uint32_t thr, float rscale, uint32_t seed) {
+                    uint32_t thr, float rscale, uint32_t seed, const uint32_t* __restrict__ salt) {
   pdl_grid_sync();
+  seed ^= step_salt(salt);
   __shared__ float sp[kWarps][kMaxLen];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wid = blockIdx.x * kWarps + warp;
@@ -114,8 +115,9 @@ __global__ void __launch_bounds__(kWarps * 32)
 attn_cls_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu, const uint8_t* __restrict__ key_valid,
                     int B, int heads, int T, const __nv_bfloat16* __restrict__ out_cls, const __nv_bfloat16* __restrict__ dout_cls,
                     const float* __restrict__ lse_cls, int lse_stride, __nv_bfloat16* __restrict__ dqkv, float scale, uint32_t thr,
-                    float rscale, uint32_t seed) {
+                    float rscale, uint32_t seed, const uint32_t* __restrict__ salt) {
   pdl_grid_sync();
+  seed ^= step_salt(salt);
   __shared__ float sp[kWarps][kMaxLen];    // dropped probabilities  -> dV
   __shared__ float sds[kWarps][kMaxLen];   // dS                     -> dK, dQ
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -186,7 +188,7 @@ extern "C" int nbest_attn_cls_fwd(nbest_ctx* ctx, const void* qkv_bf16, const in
   const int blocks = (B * heads + kWarps - 1) / kWarps;
   nbest_launch(attn_cls_fwd_kernel, dim3(blocks), dim3(kWarps * 32), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), cu_seqlens, key_valid, B, heads, T,
-      reinterpret_cast<__nv_bfloat16*>(out_cls_bf16), lse_cls, 0.125f, drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed);
+      reinterpret_cast<__nv_bfloat16*>(out_cls_bf16), lse_cls, 0.125f, drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed, nbest_salt(ctx));
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
@@ -204,7 +206,7 @@ extern "C" int nbest_attn_cls_bwd(nbest_ctx* ctx, const void* qkv_bf16, const in
   nbest_launch(attn_cls_bwd_kernel, dim3(blocks), dim3(kWarps * 32), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), cu_seqlens, key_valid, B, heads, T,
       reinterpret_cast<const __nv_bfloat16*>(out_cls_bf16), reinterpret_cast<const __nv_bfloat16*>(dout_cls_bf16), lse_cls,
-      lse_stride, reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), 0.125f, drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed);
+      lse_stride, reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), 0.125f, drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed, nbest_salt(ctx));
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }

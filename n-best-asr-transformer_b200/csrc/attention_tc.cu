@@ -216,12 +216,14 @@ struct FwdArgs {
   float* lse;
   float scale, rscale;
   uint32_t thr, seed;
+  const uint32_t* salt;   // per-step dropout salt (ptx.cuh step_salt)
 };
 
 template <bool kDrop>
 __global__ void __launch_bounds__(fwd::kThreads, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdArgs a) {
   pdl_grid_sync();
+  const uint32_t seed_eff = kDrop ? (a.seed ^ step_salt(a.salt)) : 0u;
   using namespace fwd;
   extern __shared__ __align__(1024) uint8_t smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
@@ -373,8 +375,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdArgs a) {
       }
       uint32_t vis[2], keep[2];
       const uint32_t row_base = attn_quad_row(h, a.T, t);
-      row_masks_word<kDrop>(lo, hi, kvb, a.seed, row_base, a.thr, 2 * hf, vis[0], keep[0]);
-      row_masks_word<kDrop>(lo, hi, kvb, a.seed, row_base, a.thr, 2 * hf + 1, vis[1], keep[1]);
+      row_masks_word<kDrop>(lo, hi, kvb, seed_eff, row_base, a.thr, 2 * hf, vis[0], keep[0]);
+      row_masks_word<kDrop>(lo, hi, kvb, seed_eff, row_base, a.thr, 2 * hf + 1, vis[1], keep[1]);
       bool need[2];
       need[0] = __any_sync(0xffffffffu, vis[0] != 0u);
       need[1] = __any_sync(0xffffffffu, vis[1] != 0u);
@@ -530,6 +532,7 @@ struct BwdArgs {
   __nv_bfloat16* dqkv;
   float scale, rscale;
   uint32_t thr, seed;
+  const uint32_t* salt;   // per-step dropout salt (ptx.cuh step_salt)
 };
 
 // 32 lanes x 16 consecutive fp32 columns
@@ -547,6 +550,7 @@ template <bool kDrop>
 __global__ void __launch_bounds__(bwd::kThreads, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const BwdArgs a) {
   pdl_grid_sync();
+  const uint32_t seed_eff = kDrop ? (a.seed ^ step_salt(a.salt)) : 0u;
   using namespace bwd;
   extern __shared__ __align__(1024) uint8_t smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
@@ -721,7 +725,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         kvb = dst;
       }
       uint32_t m, keep;
-      row_masks_word<kDrop>(lo, hi, kvb, a.seed, attn_quad_row(h, a.T, t), a.thr, c, m, keep);
+      row_masks_word<kDrop>(lo, hi, kvb, seed_eff, attn_quad_row(h, a.T, t), a.thr, c, m, keep);
       const uint32_t kp = keep & m;
       const bool need = __any_sync(0xffffffffu, m != 0u);
       mbar_wait(&sdp_full[b], (uint32_t)(n >> 1) & 1u);
@@ -879,6 +883,7 @@ extern "C" int nbest_attn_tiles_fwd(nbest_ctx* ctx, const void* qkv_bf16, const 
   a.rscale = 1.0f / (1.0f - p_drop);
   a.thr = drop_threshold(p_drop);
   a.seed = seed;
+  a.salt = nbest_salt(ctx);
   const int64_t items = (int64_t)max_tiles * heads;
   const int grid = (int)(items < ctx->num_sms ? items : ctx->num_sms);
   if (a.thr != 0u)
@@ -928,6 +933,7 @@ extern "C" int nbest_attn_tiles_bwd(nbest_ctx* ctx, const void* qkv_bf16, const 
   a.rscale = 1.0f / (1.0f - p_drop);
   a.thr = drop_threshold(p_drop);
   a.seed = seed;
+  a.salt = nbest_salt(ctx);
   const int64_t items = (int64_t)max_tiles * heads;
   const int grid = (int)(items < ctx->num_sms ? items : ctx->num_sms);
   if (a.thr != 0u)

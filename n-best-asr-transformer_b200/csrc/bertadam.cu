@@ -106,8 +106,14 @@ __global__ void __launch_bounds__(kThreads)
 adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                    __nv_bfloat16* __restrict__ pb, const nbest_adam_tensor* __restrict__ tensors, int n_tensors,
                    const int32_t* __restrict__ chunks, const float* __restrict__ norms, double sched, float b1, float b2,
-                   float eps, float max_grad_norm, int global_clip, float inv_bc1, float inv_sqrt_bc2) {
+                   float eps, float max_grad_norm, int global_clip, float inv_bc1, float inv_sqrt_bc2,
+                   const nbest_step_state* __restrict__ step_state) {
   pdl_grid_sync();
+  if (step_state) {   // CUDA-graph replay: this step's schedule multiplier / bias corrections come from device memory
+    sched = step_state->sched;
+    inv_bc1 = step_state->inv_bc1;
+    inv_sqrt_bc2 = step_state->inv_sqrt_bc2;
+  }
   const int ti = chunks[3 * blockIdx.x], start = chunks[3 * blockIdx.x + 1], len = chunks[3 * blockIdx.x + 2];
   const nbest_adam_tensor t = tensors[ti];
   const int64_t base = t.offset + start;
@@ -183,16 +189,18 @@ extern "C" int nbest_adam_step(nbest_ctx* ctx, int mode, float* p, const float* 
     inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, (double)step)));
   }
   auto* pb = reinterpret_cast<__nv_bfloat16*>(p_bf16);
+  // nbest_ctx_set_step_indirect: the by-value scalars are placeholders, the kernel reads the context's step-state record
+  const nbest_step_state* st = ctx->step_indirect ? ctx->step_state : nullptr;
   if (mode == NBEST_ADAM_BERT)
     nbest_launch(adam_update_kernel<NBEST_ADAM_BERT>, dim3(n_chunks), dim3(kThreads), 0, s, p, g, m, v, pb, tensors, n_tensors, chunks, norms_ws, sched,
-                                                                       b1, b2, eps, max_grad_norm, global_clip, inv_bc1, inv_sqrt_bc2);
+                                                                       b1, b2, eps, max_grad_norm, global_clip, inv_bc1, inv_sqrt_bc2, st);
   else if (mode == NBEST_ADAM_HF_ADAMW)
     nbest_launch(adam_update_kernel<NBEST_ADAM_HF_ADAMW>, dim3(n_chunks), dim3(kThreads), 0, s, p, g, m, v, pb, tensors, n_tensors, chunks, norms_ws,
                                                                            sched, b1, b2, eps, max_grad_norm, global_clip, inv_bc1,
-                                                                           inv_sqrt_bc2);
+                                                                           inv_sqrt_bc2, st);
   else
     nbest_launch(adam_update_kernel<NBEST_ADAM_TORCH>, dim3(n_chunks), dim3(kThreads), 0, s, p, g, m, v, pb, tensors, n_tensors, chunks, norms_ws, sched,
-                                                                        b1, b2, eps, max_grad_norm, global_clip, inv_bc1, inv_sqrt_bc2);
+                                                                        b1, b2, eps, max_grad_norm, global_clip, inv_bc1, inv_sqrt_bc2, st);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }

@@ -34,6 +34,14 @@ struct nbest_tmap_entry {
 constexpr int kTmapCacheSize = 1024;
 constexpr int kSchedRing = 64;        // launches in flight never share a scheduler slot
 
+// Per-step scalars a replayed CUDA graph of the training step reads from device memory (ptx.cuh step_salt; bertadam.cu).
+struct nbest_step_state {
+  uint32_t salt;        // XORed into every dropout seed
+  uint32_t indirect;    // (host mirror only) != 0: the optimizer kernels take sched / bias corrections from here
+  double sched;         // learning-rate schedule multiplier of this step
+  float inv_bc1, inv_sqrt_bc2;   // torch.optim.Adam bias corrections of this step
+};
+
 struct nbest_ctx {
   int device;
   int num_sms;
@@ -45,12 +53,16 @@ struct nbest_ctx {
   int gemm_dynamic;                    // GEMM work items drawn from a global counter (nbest_ctx_set_gemm_dynamic)
   uint32_t* sched_buf;                 // device: kSchedRing x {next item, finished units}; the ONE allocation the library owns
   uint32_t sched_seq;
+  nbest_step_state* step_state;        // device: per-step scalars (nbest_ctx_set_step_state); zero = eager behaviour
+  int step_indirect;                   // optimizer scalars come from step_state (nbest_ctx_set_step_indirect)
   uint64_t tmap_hits, tmap_misses;
   nbest_tmap_entry* tmap_cache;
   char err[512];
 };
 
 void nbest_set_error(nbest_ctx* ctx, const char* fmt, ...);
+// device address of the dropout salt (every kernel that draws dropout masks takes it next to its by-value seed)
+static inline const uint32_t* nbest_salt(const nbest_ctx* ctx) { return &ctx->step_state->salt; }
 
 #define NBEST_CHECK_ARG(ctx, cond, msg)                                        \
   do {                                                                         \

@@ -73,13 +73,16 @@ extern "C" int nbest_ctx_create(nbest_ctx** out, int device) {
     return NBEST_EINVAL;
   }
   ctx->gemm_dynamic = env_int("NBEST_GEMM_DYNAMIC", 0) != 0;
-  if (cudaMalloc(&ctx->sched_buf, kSchedRing * 2 * sizeof(uint32_t)) != cudaSuccess ||
-      cudaMemset(ctx->sched_buf, 0, kSchedRing * 2 * sizeof(uint32_t)) != cudaSuccess) {
+  // one device allocation: the GEMM scheduler ring, then the per-step state record (salt 0 = eager behaviour)
+  const size_t dev_bytes = kSchedRing * 2 * sizeof(uint32_t) + sizeof(nbest_step_state);
+  if (cudaMalloc(&ctx->sched_buf, dev_bytes) != cudaSuccess || cudaMemset(ctx->sched_buf, 0, dev_bytes) != cudaSuccess) {
     snprintf(g_create_err, sizeof(g_create_err), "cannot allocate the %zu-byte GEMM scheduler buffer", kSchedRing * 2 * sizeof(uint32_t));
     free(ctx->tmap_cache);
     free(ctx);
     return NBEST_ECUDA;
   }
+  ctx->step_state = reinterpret_cast<nbest_step_state*>(ctx->sched_buf + kSchedRing * 2);
+  ctx->step_indirect = 0;
   ctx->err[0] = 0;
   *out = ctx;
   return NBEST_OK;
@@ -102,6 +105,31 @@ extern "C" int nbest_ctx_set_gemm_dynamic(nbest_ctx* ctx, int on) {
 extern "C" int nbest_ctx_set_sm_reserve(nbest_ctx* ctx, int n_sms) {
   if (!ctx || n_sms < 0 || n_sms > ctx->num_sms - 2) return NBEST_EINVAL;
   ctx->reserve_sms = n_sms & ~1;      // CTA pairs: whole TPCs
+  return NBEST_OK;
+}
+
+namespace {
+__global__ void set_step_state_kernel(nbest_step_state* st, uint32_t salt, double sched, float inv_bc1, float inv_sqrt_bc2) {
+  st->salt = salt;
+  st->indirect = 1;
+  st->sched = sched;
+  st->inv_bc1 = inv_bc1;
+  st->inv_sqrt_bc2 = inv_sqrt_bc2;
+}
+}  // namespace
+
+extern "C" int nbest_ctx_set_step_state(nbest_ctx* ctx, uint32_t salt, double sched, float inv_bc1, float inv_sqrt_bc2,
+                                        void* stream) {
+  if (!ctx) return NBEST_EINVAL;
+  // a plain launch (no programmatic overlap): the kernels behind it read the record after their griddepcontrol.wait
+  set_step_state_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ctx->step_state, salt, sched, inv_bc1, inv_sqrt_bc2);
+  NBEST_CHECK_LAUNCH(ctx);
+  return NBEST_OK;
+}
+
+extern "C" int nbest_ctx_set_step_indirect(nbest_ctx* ctx, int on) {
+  if (!ctx) return NBEST_EINVAL;
+  ctx->step_indirect = on != 0;
   return NBEST_OK;
 }
 

@@ -170,8 +170,9 @@ embed_ln_fwd_kernel(const int32_t* __restrict__ tokens, const uint8_t* __restric
                     int T, const float* __restrict__ word, const float* __restrict__ posemb, const float* __restrict__ type,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                     __nv_bfloat16* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, uint32_t thr,
-                    float scale, uint32_t seed) {
+                    float scale, uint32_t seed, const uint32_t* __restrict__ salt) {
   pdl_grid_sync();
+  seed ^= step_salt(salt);
   const int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (t >= T) return;
   const int lane = threadIdx.x & 31;
@@ -497,9 +498,11 @@ __device__ __forceinline__ void block_reduce_cols8_atomic(const float (&acc)[CPL
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dyin, const __nv_bfloat16* __restrict__ xin, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, int T, __nv_bfloat16* __restrict__ dx,
-              __nv_bfloat16* __restrict__ dxm, uint32_t thr, float scale, uint32_t seed, float* __restrict__ dgamma,
+              __nv_bfloat16* __restrict__ dxm, uint32_t thr, float scale, uint32_t seed, const uint32_t* __restrict__ salt,
+              float* __restrict__ dgamma,
               float* __restrict__ dbeta, float* __restrict__ dbias) {
   pdl_grid_sync();
+  seed ^= step_salt(salt);
   extern __shared__ __align__(16) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t ring = smem_u32(ln_smem) + warp * (kLnStages * kLnStageBytes);
@@ -599,10 +602,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 embed_ln_bwd_kernel(const int32_t* __restrict__ tokens, const uint8_t* __restrict__ seg, const int32_t* __restrict__ pos,
                     int T, const float* __restrict__ word, const float* __restrict__ posemb, const float* __restrict__ type,
                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const __nv_bfloat16* __restrict__ dyin, uint32_t thr, float scale, uint32_t seed,
+                    const __nv_bfloat16* __restrict__ dyin, uint32_t thr, float scale, uint32_t seed, const uint32_t* __restrict__ salt,
                     float* __restrict__ dword, float* __restrict__ dpos, float* __restrict__ dtype,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, int word_pad_row, int pos_pad_row) {
   pdl_grid_sync();
+  seed ^= step_salt(salt);
   __shared__ float sh[kWarpsPerBlock * H];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 dgam[VPL], dbet[VPL], dty0[VPL], dty1[VPL];
@@ -907,7 +911,7 @@ extern "C" int nbest_embed_ln_fwd(nbest_ctx* ctx, const int32_t* tokens, const u
   if (T <= 0) return NBEST_OK;
   nbest_launch(embed_ln_fwd_kernel, dim3((T + kWarpsPerBlock - 1) / kWarpsPerBlock), dim3(kWarpsPerBlock * 32), 0, reinterpret_cast<cudaStream_t>(stream), 
       tokens, seg, pos, T, word, posemb, type, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y_bf16), mean, rstd,
-      drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed);
+      drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed, nbest_salt(ctx));
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
@@ -926,7 +930,7 @@ extern "C" int nbest_embed_ln_bwd(nbest_ctx* ctx, const int32_t* tokens, const u
   if (blocks > ctx->num_sms) blocks = ctx->num_sms;   // one block per SM (register-bound); fewer blocks = fewer column atomics
   nbest_launch(embed_ln_bwd_kernel, dim3(blocks), dim3(kWarpsPerBlock * 32), 0, reinterpret_cast<cudaStream_t>(stream), 
       tokens, seg, pos, T, word, posemb, type, gamma, mean, rstd, reinterpret_cast<const __nv_bfloat16*>(dy_bf16),
-      drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed, dword, dpos, dtype, dgamma, dbeta, word_pad_row, pos_pad_row);
+      drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed, nbest_salt(ctx), dword, dpos, dtype, dgamma, dbeta, word_pad_row, pos_pad_row);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
@@ -1001,7 +1005,7 @@ extern "C" int nbest_ln_bwd(nbest_ctx* ctx, const void* dy_bf16, const void* x_b
   nbest_launch(ln_bwd_kernel, dim3(blocks), dim3(kWarpsPerBlock * 32), kLnBwdSmem, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16), mean, rstd, gamma, T,
       reinterpret_cast<__nv_bfloat16*>(dx_bf16), p_drop > 0.f ? reinterpret_cast<__nv_bfloat16*>(dx_masked_bf16) : nullptr,
-      drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed, dgamma, dbeta, dbias);
+      drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed, nbest_salt(ctx), dgamma, dbeta, dbias);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }

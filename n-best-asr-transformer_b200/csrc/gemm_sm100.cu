@@ -54,6 +54,7 @@ struct GemmArgs {
   uint32_t drop_thresh;
   float drop_scale;
   uint32_t seed;
+  const uint32_t* salt;   // per-step dropout salt (ptx.cuh step_salt)
   uint32_t* sched;   // {next work item, finished units} of this launch (context-owned, self-resetting), or NULL = static
 };
 
@@ -288,6 +289,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     float* bias_tile = reinterpret_cast<float*>(staging + C_::kStagingBytes);
     constexpr bool kHasBias = (EPI == NBEST_EPI_BIAS || EPI == NBEST_EPI_BIAS_GELU || EPI == NBEST_EPI_BIAS_DROP_RES);
     auto unit_off = [](int row, int chunk16) { return row * 128 + ((chunk16 ^ (row & 7)) << 4); };
+    uint32_t drop_seed = 0;
+    if constexpr (EPI == NBEST_EPI_BIAS_DROP_RES) drop_seed = g.seed ^ step_salt(g.salt);
     uint32_t it = 0;
     const uint32_t tempty_remote[2] = {(CG == 2) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u,
                                        (CG == 2) ? mapa_shared(smem_u32(&tempty_bar[1]), 0) : 0u};
@@ -417,7 +420,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                   for (int j = 0; j < 32; j += 4) {
                     bool k0, k1, k2, k3;
-                    dropout_keep4(g.seed, base + j, g.drop_thresh, k0, k1, k2, k3);   // base % 4 == 0 (N, nc multiples of 32)
+                    dropout_keep4(drop_seed, base + j, g.drop_thresh, k0, k1, k2, k3);   // base % 4 == 0 (N, nc multiples of 32)
                     f2_unpack(f2_mul(f2_pack(v[j], v[j + 1]), f2_pack(k0 ? g.drop_scale : 0.f, k1 ? g.drop_scale : 0.f)), v[j], v[j + 1]);
                     f2_unpack(f2_mul(f2_pack(v[j + 2], v[j + 3]), f2_pack(k2 ? g.drop_scale : 0.f, k3 ? g.drop_scale : 0.f)), v[j + 2],
                               v[j + 3]);
@@ -678,6 +681,7 @@ extern "C" int nbest_gemm_bf16(nbest_ctx* ctx, const void* A, int64_t lda, int a
   g.ldaux = ldaux;
   g.out2 = reinterpret_cast<__nv_bfloat16*>(out2_bf16);
   g.seed = seed;
+  g.salt = nbest_salt(ctx);
   g.sched = ctx->gemm_dynamic ? ctx->sched_buf + 2 * (ctx->sched_seq++ % kSchedRing) : nullptr;
   if (p_drop > 0.f) {
     const double t = (double)p_drop * 65536.0 + 0.5;   // 16-bit threshold (ptx.cuh dropout_keep)

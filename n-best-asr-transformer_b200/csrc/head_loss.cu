@@ -36,9 +36,10 @@ __device__ __forceinline__ float bce_elem(float p, float t, float& dp) {
 __global__ void __launch_bounds__(256)
 stc_head_fwd_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ cu, int B, const float* __restrict__ W,
                     const float* __restrict__ bias, Hier h, const uint8_t* __restrict__ none_col, uint32_t thr, float rscale,
-                    uint32_t seed, float* __restrict__ cls, float* __restrict__ logits, float* __restrict__ top_scores,
+                    uint32_t seed, const uint32_t* __restrict__ salt, float* __restrict__ cls, float* __restrict__ logits, float* __restrict__ top_scores,
                     float* __restrict__ bottom_scores, float* __restrict__ final_scores, uint8_t* __restrict__ decode) {
   pdl_grid_sync();
+  seed ^= step_salt(salt);
   __shared__ float f[H];
   __shared__ float z[kMaxCols];
   __shared__ float sc[kMaxCols];   // sigmoid / softmax of z
@@ -307,8 +308,9 @@ stc_scores_bwd_kernel(const float* __restrict__ top_scores, const float* __restr
 constexpr int kWgradSplits = 8;
 __global__ void __launch_bounds__(192)
 stc_head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ cls, int B, Hier h, uint32_t thr,
-                      float rscale, uint32_t seed, float* __restrict__ dW, float* __restrict__ dbias) {
+                      float rscale, uint32_t seed, const uint32_t* __restrict__ salt, float* __restrict__ dW, float* __restrict__ dbias) {
   pdl_grid_sync();
+  seed ^= step_salt(salt);
   const int c = blockIdx.x;
   const int g = h.col_group[c];
   const int per = (B + kWgradSplits - 1) / kWgradSplits;
@@ -348,8 +350,9 @@ stc_head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict
 // per thread (one quad each) instead of once per column and feature (171 x 3 hashes before).
 __global__ void __launch_bounds__(192)
 stc_head_dgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ W, int B, Hier h, uint32_t thr,
-                      float rscale, uint32_t seed, float* __restrict__ dcls, int accumulate) {
+                      float rscale, uint32_t seed, const uint32_t* __restrict__ salt, float* __restrict__ dcls, int accumulate) {
   pdl_grid_sync();
+  seed ^= step_salt(salt);
   __shared__ float dl[kMaxCols];
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < h.n_cols; c += blockDim.x) dl[c] = dlogits[(int64_t)b * h.n_cols + c];
@@ -471,7 +474,7 @@ extern "C" int nbest_stc_head_fwd(nbest_ctx* ctx, const void* x_bf16, const int3
   NBEST_CHECK_ARG(ctx, p_drop >= 0.f && p_drop < 1.f, "p_drop out of range");
   nbest_launch(stc_head_fwd_kernel, dim3(B), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(x_bf16), cu_seqlens, B, W, bias, h, none_col_mask, drop_threshold(p_drop),
-      1.0f / (1.0f - p_drop), seed, cls, logits, top_scores, bottom_scores, final_scores, decode);
+      1.0f / (1.0f - p_drop), seed, nbest_salt(ctx), cls, logits, top_scores, bottom_scores, final_scores, decode);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }
@@ -527,10 +530,10 @@ extern "C" int nbest_stc_head_bwd(nbest_ctx* ctx, const float* dlogits, const fl
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const uint32_t thr = drop_threshold(p_drop);
   const float rscale = 1.0f / (1.0f - p_drop);
-  nbest_launch(stc_head_wgrad_kernel, dim3(dim3(h.n_cols, kWgradSplits)), dim3(192), 0, s, dlogits, cls, B, h, thr, rscale, seed, dW, dbias);
+  nbest_launch(stc_head_wgrad_kernel, dim3(dim3(h.n_cols, kWgradSplits)), dim3(192), 0, s, dlogits, cls, B, h, thr, rscale, seed, nbest_salt(ctx), dW, dbias);
   NBEST_CHECK_LAUNCH(ctx);
   NBEST_CHECK_ARG(ctx, h.n_groups + 1 <= 16, "at most 15 multi-way value groups (4 keep bits per group in one word)");
-  nbest_launch(stc_head_dgrad_kernel, dim3(B), dim3(192), 0, s, dlogits, W, B, h, thr, rscale, seed, dcls, accumulate_dcls);
+  nbest_launch(stc_head_dgrad_kernel, dim3(B), dim3(192), 0, s, dlogits, W, B, h, thr, rscale, seed, nbest_salt(ctx), dcls, accumulate_dcls);
   NBEST_CHECK_LAUNCH(ctx);
   return NBEST_OK;
 }

@@ -24,6 +24,18 @@ __device__ __forceinline__ void pdl_grid_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- per-step state (CUDA-graph replay)
+// A captured graph of the training step bakes every by-value kernel argument in, the dropout seeds among them. What must
+// change from one replay to the next lives in a small device-side record owned by the context (common.h nbest_step_state,
+// written by nbest_ctx_set_step_state on the stream ahead of the graph): every dropout kernel XORs `salt` into its seed
+// (0 outside graph replay: the by-value seed alone decides), the optimizer reads its schedule multiplier from it.
+// Read AFTER pdl_grid_sync (the writer may be the kernel right before this one) and past L1 (.cg).
+__device__ __forceinline__ uint32_t step_salt(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -617,34 +617,52 @@ class TOD_ASR_Transformer_STC(nn.Module):
     # ------------------------------------------------------------------------------------------------ public: fused step
     @ops.with_bound_stream
     def forward_loss_backward(self, input_ids, labels, trans_input_ids=None, seg_ids=None, trans_seg_ids=None,
-                              add_l2_loss=False, mse_scale=1.0, input_lens=None, trans_input_lens=None, backward=True):
+                              add_l2_loss=False, mse_scale=1.0, input_lens=None, trans_input_lens=None, backward=True,
+                              n_real=None):
         """Fused training path: model forward + cal_total_loss (n_best_asr_bert.py:160-195) + backward in our kernels.
 
         Returns (losses, head) where losses is a device fp32 tensor [mse, bce_final, bce_top, ce] (no host sync) and head
         carries top/bottom/final scores and the decode bitmap. total = losses.sum(); loss_record = total / B.
-        mse_scale lets a data-parallel trainer scale the mean-reduced MSE term by 1/world_size."""
+        mse_scale lets a data-parallel trainer scale the mean-reduced MSE term by 1/world_size.
+        n_real: only the first n_real utterances are real; the rows behind them are FILLER sequences that quantise the
+        batch's token counts for CUDA-graph replay (graph.add_fillers). They run through the encoder like any sequence
+        but take no part in the loss: labels is [n_real, n_bottom], their loss gradient is exactly zero, and so is
+        everything the backward accumulates for them."""
         nb = self.hier.n_bottom
+        Br = input_ids.shape[0] if n_real is None else int(n_real)
+        if not 0 < Br <= input_ids.shape[0]:
+            raise ValueError("n_real=%d outside (0, B=%d]" % (Br, input_ids.shape[0]))
         if not (torch.is_tensor(labels) and labels.is_cuda and labels.dtype == torch.float32 and labels.dim() == 2
-                and labels.shape == (input_ids.shape[0], nb) and labels.is_contiguous()):
+                and labels.shape == (Br, nb) and labels.is_contiguous()):
             raise ValueError("labels must be a contiguous CUDA float32 [B=%d, %d] multi-hot tensor (collate_fn, "
-                             "tod_asr_util.py:118-130), got %s" % (input_ids.shape[0], nb, _describe(labels)))
+                             "tod_asr_util.py:118-130), got %s" % (Br, nb, _describe(labels)))
         self._step_seed += 1
         pk = self._pack_streams(input_ids, seg_ids, trans_input_ids, trans_seg_ids, input_lens, trans_input_lens)
         sv = self._encode(pk, save=backward)
         B = pk.B_asr
         ho = self._head_forward(sv, B)
+        ho.n_real = Br
         dev = self.device
         losses = ops.zero_(torch.empty(4, device=dev, dtype=torch.float32))
         dlogits = torch.empty((B, self.hier.n_cols), device=dev, dtype=torch.float32)
         use_l2 = add_l2_loss and trans_input_ids is not None
         trans_cls = d_asr = d_trans = None
         if trans_input_ids is not None:
+            if pk.B - B < B:
+                raise ValueError("the transcript stream has fewer rows (%d) than the ASR stream (%d)" % (pk.B - B, B))
             trans_cls = self._cls_rows(sv, B, B)      # the reference always computes it (models/model.py:51-58)
         if use_l2:
             d_asr = torch.empty((B, H), device=dev, dtype=torch.float32)
             d_trans = torch.empty((B, H), device=dev, dtype=torch.float32)
-        ops.stc_loss_fwd_bwd(ho.logits, labels, self.hier, losses, dlogits, ho.cls if use_l2 else None,
-                             trans_cls if use_l2 else None, mse_scale, d_asr, d_trans)
+        if Br < B:                                    # filler rows: zero loss gradient
+            ops.zero_(dlogits[Br:])
+            if use_l2:
+                ops.zero_(d_asr[Br:])
+                ops.zero_(d_trans[Br:])
+        R = (lambda t: t[:Br]) if Br < B else (lambda t: t)
+        ops.stc_loss_fwd_bwd(R(ho.logits), labels, self.hier, losses, R(dlogits), R(ho.cls) if use_l2 else None,
+                             R(trans_cls) if use_l2 else None, mse_scale, R(d_asr) if use_l2 else None,
+                             R(d_trans) if use_l2 else None)
         if backward:
             self._backward_from_dlogits(sv, ho, dlogits, d_asr, d_trans)
         ho.trans_cls = trans_cls

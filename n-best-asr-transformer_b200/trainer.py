@@ -232,7 +232,7 @@ class DataParallelTrainer:
             self.optimizer.step_bucket(name)
 
     @ops.with_bound_stream
-    def accumulate(self, ids, labels, trans_ids=None, seg=None, trans_seg=None, lens=None, trans_lens=None):
+    def accumulate(self, ids, labels, trans_ids=None, seg=None, trans_seg=None, lens=None, trans_lens=None, n_real=None):
         """Forward + loss + backward of one micro-batch INTO the flat gradient buffer, without exchange or update: the
         first n_accum_steps - 1 micro-batches of the reference's gradient accumulation (n_best_asr_bert.py:264-266; the
         wgrad kernels accumulate with fp32 red.add, so nothing else is needed). The micro-batch that completes the
@@ -240,15 +240,17 @@ class DataParallelTrainer:
         m = self.model
         m._grad_ready_hook = None
         losses, head = m.forward_loss_backward(ids, labels, trans_ids, seg, trans_seg, add_l2_loss=self.add_l2_loss,
-                                               mse_scale=1.0 / self.world, input_lens=lens, trans_input_lens=trans_lens)
+                                               mse_scale=1.0 / self.world, input_lens=lens, trans_input_lens=trans_lens,
+                                               n_real=n_real)
         self.last_head = head
         return losses
 
     @ops.with_bound_stream
     def step(self, ids, labels, trans_ids=None, seg=None, trans_seg=None, lens=None, trans_lens=None, clip_norm=None,
-             scheduler=None):
+             scheduler=None, n_real=None):
         """clip_norm: global gradient-norm clip folded into an AdamW / Adam update (n_best_asr_bert.py:268-271);
-        scheduler: stepped after the update (adamw branch, :276-277)."""
+        scheduler: stepped after the update (adamw branch, :276-277); n_real: rows behind it are shape fillers
+        (graph.add_fillers; model.forward_loss_backward)."""
         m = self.model
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())     # zeroed grads / previous step are visible
@@ -261,7 +263,8 @@ class DataParallelTrainer:
         self._pending = []
         try:
             losses, head = m.forward_loss_backward(ids, labels, trans_ids, seg, trans_seg, add_l2_loss=self.add_l2_loss,
-                                                   mse_scale=1.0 / self.world, input_lens=lens, trans_input_lens=trans_lens)
+                                                   mse_scale=1.0 / self.world, input_lens=lens, trans_input_lens=trans_lens,
+                                                   n_real=n_real)
         finally:
             m._grad_ready_hook = None
         for n in self._pending:                          # (only if the backward never announced "emb")

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), "libnbest_sm100.so does not export %s" % name
     assert sorted(_lib.exported_symbols()) == declared, "ctypes signature table and header disagree"
     lib.nbest_abi_version.restype = ctypes.c_int
-    assert lib.nbest_abi_version() == 2
+    assert lib.nbest_abi_version() == 3
 
 
 def test_header_cites_reference_for_every_entry_point():
