@@ -14,6 +14,7 @@ but every device operation runs in the hand-written sm_100a kernels of libnbest_
 
 There is no CPU / eager fallback: constructing the model without an sm_100 GPU raises.
 """
+import os
 from collections import OrderedDict
 from dataclasses import dataclass
 
@@ -148,6 +149,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
         self.hier = ops.DeviceHierarchy(top2bottom, none_bottoms, device=device)
         self.top2bottom_dict = self.hier.top2bottom
         self._step_seed = int(seed)
+        self.defer_low_wgrad = int(os.environ.get("NBEST_DEFER_WGRAD", "1"))     # lowest layers whose wgrads are deferred, see _encoder_backward
         self._seed_salt = 0      # data-parallel rank salt (trainer): ranks draw independent dropout masks
         # The head (and the MSE term) only ever read the [CLS] row of the last hidden state (reference models/model.py:
         # 46-47,58), so the last layer's attention output, out-projection, FFN and LayerNorms are computed for that row
@@ -156,7 +158,6 @@ class TOD_ASR_Transformer_STC(nn.Module):
         self.cls_only_last_layer = True
         # Attention of sequences <= 128 tokens on the tcgen05 / TMEM / TMA tile kernels (csrc/attention_tc.cu); longer ones
         # (10-best inference) keep the block-loop kernels of csrc/attention.cu. NBEST_ATTN_TC=0: everything on the latter.
-        import os
         self.attn_tensor_path = os.environ.get("NBEST_ATTN_TC", "1") != "0"
         self._build_params(encoder_state, seed)
 
@@ -463,6 +464,12 @@ class TOD_ASR_Transformer_STC(nn.Module):
         delta = torch.empty((s.heads, T_act), device=dev, dtype=torch.float32)     # written by the out-proj dgrad (EPI_DELTA)
         A = lambda t: t[:T_act]
         ws = {}       # per-row-count workspaces of the post-attention block: {n: (dpre, dprem, du, dx1, dctx)}
+        # The weight-gradient GEMMs of the LOWEST layer(s) are issued after the embedding backward instead of inside the
+        # layer: nothing downstream needs them, and in a data-parallel run the embedding bucket — the largest one, and the
+        # last the backward can finish — then has its all-reduce and update running under ~0.2 ms of GEMMs per deferred layer
+        # instead of after the last kernel of the step (profiles/r2_dp_timeline_*.log). Same kernels, same operands:
+        # results are unchanged; a deferred layer keeps its own dm / du / dqkv buffers alive until then.
+        deferred = []         # [(layer, dqkv, [(args, kwargs) of its wgrad GEMMs])], highest layer first
         for l in reversed(range(s.layers)):
             w, L = self._w[l], sv.layers[l]
             compact = sv.cls_compact and l == s.layers - 1       # this layer's tail ran on one CLS row per sequence
@@ -470,6 +477,12 @@ class TOD_ASR_Transformer_STC(nn.Module):
             if n not in ws:
                 ws[n] = (bf(n, H), (bf(n, H) if p_h > 0 else None), bf(n, s.intermediate), bf(n, H), bf(n, H))
             dpre, dprem, du, dx1, dctx = ws[n]
+            defer = l < self.defer_low_wgrad and not compact
+            if defer:
+                dpre, dprem, du = bf(n, H), (bf(n, H) if p_h > 0 else None), bf(n, s.intermediate)
+                dqkv = bf(T_act, 3 * H)
+                deferred.append((l, dqkv, []))
+            wgrad = (lambda *a, **k: deferred[-1][2].append((a, k))) if defer else ops.gemm
             R = lambda t: t[:n]
             # ---- FFN block
             ops.ln_bwd(dx, R(L.pre2), L.mean2, L.rstd2, w["p_g2"], dpre, w["g_g2"], w["g_b2"], dx_masked=dprem,
@@ -477,9 +490,11 @@ class TOD_ASR_Transformer_STC(nn.Module):
             dm = dprem if p_h > 0 else dpre
             # du = (dm W2) * gelu'(u), and in the same epilogue the FFN-in bias gradient g_bi += column sums of du
             ops.gemm(dm, w["h_w2"], b_mn_major=True, epilogue=ops.EPI_DGELU, aux=R(L.u), out=du, out2=w["g_bi"])
-            ops.gemm(dm, R(L.g), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_w2"])
+            wgrad(dm, R(L.g), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_w2"])
             ops.gemm(du, w["h_w1"], b_mn_major=True, epilogue=ops.EPI_ADD, aux=dpre, out=dx1)              # + residual grad
-            ops.gemm(du, R(L.x1), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_w1"])
+            wgrad(du, R(L.x1), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_w1"])
+            if defer:        # the FFN block's dm stays alive for its deferred wgrad: the attention block gets buffers of its own
+                dpre, dprem = bf(n, H), (bf(n, H) if p_h > 0 else None)
             # ---- attention block
             ops.ln_bwd(dx1, R(L.pre1), L.mean1, L.rstd1, w["p_g1"], dpre, w["g_g1"], w["g_b1"], dx_masked=dprem,
                        dbias=w["g_bo"], p_drop=p_h, seed=self._seed(l, 2), T=n)
@@ -488,7 +503,7 @@ class TOD_ASR_Transformer_STC(nn.Module):
                 ops.gemm(dm, w["h_wo"], b_mn_major=True, epilogue=ops.EPI_NONE, out=dctx)
             else:      # dO = dm Wo, and in the same epilogue the attention backward's delta = rowsum(dO * O) per head
                 ops.gemm(dm, w["h_wo"], b_mn_major=True, epilogue=ops.EPI_DELTA, aux=R(L.ctx), out=dctx, out2=delta[:, :n])
-            ops.gemm(dm, R(L.ctx), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_wo"])
+            wgrad(dm, R(L.ctx), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_wo"])
             # a window of short, non-persistent kernels (attention backward): the data-parallel trainer starts the pending
             # gradient all-reduces here, so that they run next to kernels that shrink gracefully instead of next to the
             # persistent GEMMs, whose CTA pairs would have to wait for the SMs the collective occupies
@@ -511,14 +526,20 @@ class TOD_ASR_Transformer_STC(nn.Module):
                                  T_active=T_act, sum_l2=l2s)
                 dres = dpre
             ops.gemm(dqkv, w["h_wqkv"], b_mn_major=True, epilogue=ops.EPI_ADD, aux=dres, out=dx)   # (full path: dx was consumed above)
-            ops.gemm(dqkv, A(L.x_in), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_wqkv"])
-            ops.colsum(dqkv, w["g_bqkv"], T=T_act)
-            self._notify("layer%d" % l)
+            wgrad(dqkv, A(L.x_in), a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_ACCUM_F32, out=w["g_wqkv"])
+            if not defer:
+                ops.colsum(dqkv, w["g_bqkv"], T=T_act)
+                self._notify("layer%d" % l)
         em = self._emb
         ops.embed_ln_bwd(pk, em["p_word"], em["p_pos"], em["p_type"], em["p_gamma"], sv.mean0, sv.rstd0, dx, em["g_word"],
                          em["g_pos"], em["g_type"], em["g_gamma"], em["g_beta"], p_h, self._seed(0, 15),
                          word_pad_row=s.pad_token_id, pos_pad_row=1 if s.roberta_style else -1, T=T_act)
         self._notify("emb")
+        for l, dqkv_l, calls in deferred:
+            for a, k in calls:
+                ops.gemm(*a, **k)
+            ops.colsum(dqkv_l, self._w[l]["g_bqkv"], T=T_act)
+            self._notify("layer%d" % l)
 
     def _notify(self, bucket):
         """Tell the data-parallel trainer that every gradient kernel of `bucket` has been enqueued."""

@@ -35,6 +35,7 @@ class GradBucketer:
         self.comm_stream = comm_stream
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self._pending = []
+        self.stamp = None             # optional callable(tag, stream): the trainer's timeline recorder
 
     def reduce(self, name):
         """Enqueue the all-reduce of one bucket. CUDA: on the comm stream, after everything enqueued so far on the
@@ -50,7 +51,11 @@ class GradBucketer:
             ev.record(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
+                if self.stamp:
+                    self.stamp("allreduce_start:" + name, self.comm_stream)
                 dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+                if self.stamp:
+                    self.stamp("allreduce_end:" + name, self.comm_stream)
         else:
             self._pending.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
@@ -133,6 +138,7 @@ class DataParallelTrainer:
         self.bucketer = GradBucketer(model.flat.grads, segments, group, self.comm_stream)
         self.group = group
         self._pending = []
+        self._emb_seen = False
         # BertAdam per bucket on a side stream, each bucket as soon as its (all-reduced) gradients are final: the HBM-bound
         # update of layer l then runs under the tensor-bound backward GEMMs of the layers below it instead of after them
         # (single GPU: measured neutral — the update competes with the wgrad GEMMs for HBM — so it is on by default only
@@ -170,17 +176,47 @@ class DataParallelTrainer:
         if self.overlap_optimizer:
             optimizer.set_buckets(segments)
             self.opt_stream = torch.cuda.Stream(device=model.device)
+        self.timeline = None          # start_timeline(): [(tag, CUDA event)] of one step (profiles/dp_timeline.py)
+
+    # ------------------------------------------------------------------ per-bucket timeline (diagnostics)
+    def start_timeline(self):
+        """Record CUDA events at the backward's bucket / slot announcements (main stream), around every bucket's all-reduce
+        (comm stream) and BertAdam update (optimizer stream) of the steps that follow; stop_timeline() returns
+        [(tag, ms since the step started)]."""
+        self.timeline = []
+        self.bucketer.stamp = self._stamp
+
+    def _stamp(self, tag, stream=None):
+        if self.timeline is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream if stream is not None else torch.cuda.current_stream())
+            self.timeline.append((tag, ev))
+
+    def stop_timeline(self):
+        torch.cuda.synchronize()
+        tl, self.timeline = self.timeline, None
+        self.bucketer.stamp = None
+        if not tl:
+            return []
+        t0 = tl[0][1]
+        return [(tag, t0.elapsed_time(ev)) for tag, ev in tl]
 
     def _grad_ready(self, name):
+        if self.timeline is not None:
+            self._stamp("backward:" + name)
         if self.comm_slots:
             if name == "slot" or name == "emb":
                 if name == "emb":
                     self._pending.append(name)
+                    self._emb_seen = True
                 pending, self._pending = self._pending, []
                 for n in pending:
                     self._launch_bucket(n)
             elif name in self._bucket_names:
-                self._pending.append(name)
+                if self._emb_seen:       # the lowest layer's deferred weight gradients: no later slot will come
+                    self._launch_bucket(name)
+                else:
+                    self._pending.append(name)
             return
         if name != "slot":
             self._launch_bucket(name)
@@ -229,7 +265,11 @@ class DataParallelTrainer:
         ev.record(self.comm_stream if self.world > 1 else torch.cuda.current_stream())
         self.opt_stream.wait_event(ev)
         with ops.on_stream(self.opt_stream):
+            if self.timeline is not None:
+                self._stamp("adam_start:" + name, self.opt_stream)
             self.optimizer.step_bucket(name)
+            if self.timeline is not None:
+                self._stamp("adam_end:" + name, self.opt_stream)
 
     @ops.with_bound_stream
     def accumulate(self, ids, labels, trans_ids=None, seg=None, trans_seg=None, lens=None, trans_lens=None, n_real=None):
@@ -261,6 +301,9 @@ class DataParallelTrainer:
         else:
             m._grad_ready_hook = self._grad_ready if self.world > 1 else None
         self._pending = []
+        self._emb_seen = False
+        if self.timeline is not None:
+            self._stamp("step_start")
         try:
             losses, head = m.forward_loss_backward(ids, labels, trans_ids, seg, trans_seg, add_l2_loss=self.add_l2_loss,
                                                    mse_scale=1.0 / self.world, input_lens=lens, trans_input_lens=trans_lens,
@@ -282,6 +325,8 @@ class DataParallelTrainer:
         if scheduler is not None:
             scheduler.step()
         self.optimizer.zero_grad()
+        if self.timeline is not None:
+            self._stamp("step_end")
         self.last_head = head
         return losses
 

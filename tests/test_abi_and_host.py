@@ -174,17 +174,20 @@ def test_dropout_hash_restatement_is_a_sound_bernoulli_source():
 
 def test_trainer_launches_every_bucket_once_at_the_announced_slots():
     """DataParallelTrainer._grad_ready (host logic, no GPU): with collective slots a finished bucket waits for the next
-    'slot' the backward announces (or for 'emb', the last notification) and is launched exactly once, in completion order;
-    without slots it is launched immediately; names that are not buckets ('head', layers inside a merged bucket) are ignored."""
+    'slot' the backward announces (or for 'emb') and is launched exactly once, in completion order; the lowest layer's
+    bucket — its weight-gradient GEMMs are issued AFTER the embedding backward (model._encoder_backward) — is announced
+    behind 'emb' and launched at once; without slots everything is launched immediately; names that are not buckets
+    ('head', layers inside a merged bucket) are ignored."""
     from nbest_b200.trainer import DataParallelTrainer
     events = ["head"]
-    for l in reversed(range(4)):
+    for l in reversed(range(1, 4)):
         events += ["slot", "layer%d" % l]
-    events.append("emb")
+    events += ["slot", "emb", "layer0"]
 
     def run(slots, buckets):
         t = object.__new__(DataParallelTrainer)
         t.comm_slots, t._pending, t._bucket_names, launched = slots, [], set(buckets), []
+        t.timeline, t._emb_seen = None, False
         t._launch_bucket = lambda name: launched.append((name, len(seen)))
         seen = []
         for e in events:
@@ -192,15 +195,16 @@ def test_trainer_launches_every_bucket_once_at_the_announced_slots():
             t._grad_ready(e)
         return launched
 
-    one = ["layer3", "layer2", "layer1", "layer0", "emb"]
+    one = ["layer3", "layer2", "layer1", "emb", "layer0"]
     got = run(True, one)
     assert [n for n, _ in got] == one
-    # layer3's bucket starts at the slot announced before layer2's backward window, ..., layer0 and emb at the very end
+    # layer3's bucket starts at the slot announced before layer2's backward window, ..., emb when it is announced, layer0 last
     pos = {n: i for n, i in got}
-    assert events[pos["layer3"] - 1] == "slot" and events[pos["layer1"] - 1] == "slot" and pos["layer0"] == pos["emb"] == len(events)
+    assert events[pos["layer3"] - 1] == "slot" and events[pos["layer1"] - 1] == "slot"
+    assert events[pos["emb"] - 1] == "emb" and events[pos["layer0"] - 1] == "layer0" and pos["layer0"] == len(events)
     got = run(False, one)
     assert [n for n, _ in got if n in one] == one and all(events[i - 1] == n for n, i in got)      # immediately
-    two = ["layer2", "layer0", "emb"]                                  # two layers per bucket: named after the last to finish
+    two = ["layer2", "emb", "layer0"]                                  # two layers per bucket: named after the last to finish
     assert [n for n, _ in run(True, two)] == two
 
 
