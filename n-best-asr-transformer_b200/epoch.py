@@ -148,7 +148,9 @@ def train_epoch(model, data, opt, memory, trainer=None):
     batchSize, :522-556), the batches in between only accumulate gradients; a trailing incomplete group is dropped by
     the zero_grad at the next epoch start exactly as in the reference (:236). `opt.optim_choice` selects what happens at
     a step (:268-277): bertadam -> step; adam -> global clip at opt.max_norm + step; adamw -> clip + step +
-    opt.scheduler.step(). Metrics and losses accumulate on the device."""
+    opt.scheduler.step(). Metrics and losses accumulate on the device.
+    `opt.cuda_graphs = True` (one GPU, bertadam) replays the optimizer steps as CUDA graphs (graph.GraphedTrainer): filler
+    sequences round each batch's token counts to `opt.graph_bucket = (n_fill, multiple)` so that batches share graphs."""
     from .inputs import prepare_inputs_for_roberta
     from .trainer import DataParallelTrainer
     model.train()
@@ -162,15 +164,26 @@ def train_epoch(model, data, opt, memory, trainer=None):
     choice = str(getattr(opt, "optim_choice", "bertadam")).lower()
     clip = float(getattr(opt, "max_norm", 0.0)) if choice != "bertadam" else None
     sched = getattr(opt, "scheduler", None) if choice == "adamw" else None
+    graphed = None
+    if bool(getattr(opt, "cuda_graphs", False)) and choice == "bertadam" and trainer.world == 1:
+        from .graph import GraphedTrainer
+        graphed = getattr(opt, "_nbest_graphed", None)
+        if graphed is None or graphed.trainer is not trainer:
+            graphed = GraphedTrainer(trainer, bucket=tuple(getattr(opt, "graph_bucket", (3, 256))),
+                                     width=getattr(opt, "graph_width", None))
+            opt._nbest_graphed = graphed
     metrics = EpochMetrics(model.device)
     for step, batch in enumerate(data):
         labels, _, _, ids, seg, lens, tids, tseg, tlens = _inputs(batch, opt, prepare_inputs_for_roberta)
         labels = labels.to(model.device, non_blocking=True)
-        if (step + 1) % n_accum == 0:
-            losses = trainer.step(ids, labels, tids, seg, tseg, lens, tlens, clip_norm=clip, scheduler=sched)
-        else:
+        if (step + 1) % n_accum != 0:
             losses = trainer.accumulate(ids, labels, tids, seg, tseg, lens, tlens)
-        metrics.update(trainer.last_head.decode, labels, losses)
+        elif graphed is not None:
+            losses = graphed.step(ids, labels, tids, seg, tseg, lens, tlens)
+        else:
+            losses = trainer.step(ids, labels, tids, seg, tseg, lens, tlens, clip_norm=clip, scheduler=sched)
+        # (a graphed step's head carries the filler rows behind the batch's own: the metrics see the real ones)
+        metrics.update(trainer.last_head.decode[:labels.shape[0]], labels, losses)
     return metrics.result()
 
 

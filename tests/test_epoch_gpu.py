@@ -160,6 +160,29 @@ def test_train_epoch_checkpoint_and_resume_are_continuous(tmp_path):
     assert torch.equal(model_c.flat.params, model.flat.params)
 
 
+def test_train_epoch_with_cuda_graphs_matches_the_eager_epoch():
+    """opt.cuda_graphs: the epoch's optimizer steps replayed as CUDA graphs over filler-bucketed batches give the epoch the
+    eager loop gives — mean loss, P / R / F counters, accuracy (dropout off; fillers and graph replay change rounding only),
+    and the second epoch replays the graphs the first one captured (the fixture's four 12-utterance batches differ in
+    token count and two of them hold sequences above 128 tokens: four shapes)."""
+    from nbest_b200 import epoch as E
+    model, optim, opt, memory, meta, raw_in, raw_trans, *_ = _setup()
+    model_g, optim_g, opt_g, *_ = _setup()
+    data = _batches(E, meta, raw_in, raw_trans, 12)
+    opt_g.cuda_graphs, opt_g.graph_bucket, opt_g.graph_width = True, (4, 256), 256
+    for ep in range(2):
+        l, prf, acc = E.train_epoch(model, data, opt, memory)
+        lg, prfg, accg = E.train_epoch(model_g, data, opt_g, memory)
+        assert abs(l - lg) / abs(l) < 2e-3, (ep, l, lg)
+        assert abs(acc - accg) <= 100.0 / 48 * 2 and max(abs(a - b) for a, b in zip(prf, prfg)) <= 5.0, (prf, prfg, acc, accg)
+    gt = opt_g._nbest_graphed
+    assert gt.capture_error is None and gt.eager_steps == 1 and gt.replays == 2 * len(data) - 1
+    assert gt.captures <= len(data), gt.captures
+    assert optim_g._steps == optim._steps
+    cos = lambda a, b: float((a.double() @ b.double()) / (a.double().norm() * b.double().norm()))
+    assert cos(model_g.flat.params, model.flat.params) > 1 - 2e-5
+
+
 def test_prefetcher_feeds_the_trainer_from_pretokenized_data(tmp_path):
     from nbest_b200 import data as D, epoch as E
     from nbest_b200.trainer import DataParallelTrainer
