@@ -272,8 +272,17 @@ def main():
     kind = "xlm-roberta" if args.model == "xlmr" else "bert"
     spec = mk() if drop is None else mk(hidden_dropout=0.0, attn_dropout=0.0)
     infer = args.mode == "infer"
+    # data-parallel: the flat gradient buffer lives in NCCL-registered memory (zero-copy NVLS all-reduce)
+    from nbest_b200.trainer import NcclGradPool
+    gpool = NcclGradPool(dev) if (world > 1 and not infer) else None
+    if gpool is not None:
+        gpool.__enter__()
     model = TOD_ASR_Transformer_STC(spec=spec, top2bottom=t2b, dropout=0.3 if drop is None else 0.0, device=dev,
                                     none_bottoms=hj["none_bottoms"], seed=999)
+    if gpool is not None:
+        gpool.__exit__()
+        gpool.register()
+        print("rank %d: gradient buffer in NCCL-registered memory: %s %s" % (rank, gpool.ok, gpool.why or ""), file=sys.stderr)
     model.train(not infer)
     groups = []
     for n, p in model.named_parameters():                          # reference n_best_asr_bert.py:535-550
@@ -475,6 +484,7 @@ def main():
             config=dict(workload=workload_name(args),
                 global_batch=world * args.batch, tokens_per_step_asr=float(T), tokens_per_step_transcript=float(Tt),
                 parallelism=("replicas%d" if infer else "dp%d") % world,
+                nccl_registered_grads=bool(gpool is not None and gpool.ok),
                 dropout="off" if (args.no_dropout or infer) else "0.1/0.1/0.3",
                 streams="asr forward + decode (eval mode)" if infer else "asr fwd+bwd, transcript %s" % (
                     "fwd+bwd" if args.l2 else ("skipped (--skip-transcript)" if skip_t else "fwd only (as the reference)")),

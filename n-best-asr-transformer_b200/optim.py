@@ -61,6 +61,9 @@ def build_adam_tables(spec, device, chunk=16384):
                 norms=torch.zeros(n + len(chunks), dtype=torch.float32, device=device))
 
 
+GRAD_POOL = None      # a torch.cuda.MemPool the next FlatBuffers allocates its gradient buffer from (trainer.NcclGradPool)
+
+
 class FlatBuffers:
     """One flat fp32 buffer each for parameters, gradients and the two Adam moments (+ optional bf16 working copy)."""
 
@@ -77,7 +80,13 @@ class FlatBuffers:
         self.total = total
         self.shapes = [tuple(s) for s in shapes]
         self.params = torch.zeros(total, dtype=torch.float32, device=device)
-        self.grads = torch.zeros(total, dtype=torch.float32, device=device)
+        if GRAD_POOL is not None and torch.device(device).type == "cuda":
+            # data-parallel runs: the buffer every gradient all-reduce works on comes from NCCL's own allocator and is
+            # registered with the communicator (zero-copy NVLS collectives, see trainer.NcclGradPool)
+            with torch.cuda.use_mem_pool(GRAD_POOL, device=torch.device(device)):
+                self.grads = torch.zeros(total, dtype=torch.float32, device=device)
+        else:
+            self.grads = torch.zeros(total, dtype=torch.float32, device=device)
         self.bf16 = torch.zeros(total, dtype=torch.bfloat16, device=device) if with_bf16 else None
         self.m = None
         self.v = None

@@ -10,11 +10,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nbest_b200.model import EncoderSpec, TOD_ASR_Transformer_STC
 from nbest_b200.optim import BertAdam
 from nbest_b200.synth import synth_batch
-from nbest_b200.trainer import DataParallelTrainer, init_distributed
+from nbest_b200.trainer import DataParallelTrainer, NcclGradPool, init_distributed
 rank, local, world = init_distributed()
+pool = NcclGradPool("cuda:%d" % local)
 hj = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests/golden/dstc2_hierarchy.json")))
-model = TOD_ASR_Transformer_STC(spec=EncoderSpec.bert_base(), top2bottom={int(k): v for k, v in hj["top2bottom"].items()},
-                                dropout=0.3, device="cuda:%d" % local, none_bottoms=hj["none_bottoms"])
+with pool:
+    model = TOD_ASR_Transformer_STC(spec=EncoderSpec.bert_base(), top2bottom={int(k): v for k, v in hj["top2bottom"].items()},
+                                    dropout=0.3, device="cuda:%d" % local, none_bottoms=hj["none_bottoms"])
+pool.register()
 model.train()
 opt = BertAdam([dict(params=p, lr=3e-5, weight_decay=0.01) for p in model.parameters()], lr=3e-5, warmup=0.1, t_total=2300)
 tr = DataParallelTrainer(model, opt)
@@ -35,6 +38,7 @@ tr.start_timeline()
 step()
 tl = tr.stop_timeline()
 if rank == 0:
+    print("# gradient buffer in NCCL-registered memory: %s %s" % (pool.ok, pool.why or ""))
     print("# %d x B200, B = 256 per GPU; step without stamps %.3f ms; buckets: %s" % (
         world, plain, ", ".join("%s %.0f MB" % (n, (e - s) * 4 / 2**20) for n, s, e in tr.bucketer.segments)))
     print("# tag                               ms since step start")
