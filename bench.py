@@ -423,7 +423,7 @@ def main():
             step_graph_host(i)
         ms_e2e_g, _, last_g = timed(step_graph_host, args.steps)
         modes["graph"] = dict(ms_per_step=ms_g / args.steps, e2e_ms_per_step=ms_e2e_g / args.steps, gpu_launches=int(launches_g),
-                              graphs_captured=gt.captures, replays=gt.replays, eager_fallbacks=gt.eager_steps - 1,
+                              graphs_captured=gt.captures, replays=gt.replays, eager_fallbacks=gt.eager_steps,
                               capture_error=gt.capture_error, h2d_bytes_per_step=h2d_bytes_graph,
                               shape_buckets="%d filler sequences per stream, token counts rounded up to multiples of %d "
                                             "(appended by the data pipeline ahead of the timed region)" % (n_fill, mult))

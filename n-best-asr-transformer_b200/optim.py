@@ -83,7 +83,10 @@ class FlatBuffers:
         if GRAD_POOL is not None and torch.device(device).type == "cuda":
             # data-parallel runs: the buffer every gradient all-reduce works on comes from NCCL's own allocator and is
             # registered with the communicator (zero-copy NVLS collectives, see trainer.NcclGradPool)
-            with torch.cuda.use_mem_pool(GRAD_POOL, device=torch.device(device)):
+            try:
+                with torch.cuda.use_mem_pool(GRAD_POOL, device=torch.device(device)):
+                    self.grads = torch.zeros(total, dtype=torch.float32, device=device)
+            except Exception:         # best effort: NCCL's allocator refused (no multicast support, ...) -> ordinary memory
                 self.grads = torch.zeros(total, dtype=torch.float32, device=device)
         else:
             self.grads = torch.zeros(total, dtype=torch.float32, device=device)
