@@ -208,6 +208,20 @@ def test_trainer_launches_every_bucket_once_at_the_announced_slots():
     assert [n for n, _ in run(True, two)] == two
 
 
+def test_nccl_grad_pool_is_best_effort_without_nccl():
+    """trainer.NcclGradPool (gradient buffer in NCCL-registered memory) degrades to ordinary allocation when there is no
+    NCCL communicator: nothing raises, `ok` is False with a reason, and FlatBuffers allocates as usual inside `with pool`."""
+    from nbest_b200 import optim
+    from nbest_b200.trainer import NcclGradPool
+    pool = NcclGradPool("cpu")
+    assert pool.ok is False and pool.why
+    with pool:
+        assert optim.GRAD_POOL is None
+        fb = optim.FlatBuffers([(4, 8), (8,)], "cpu", with_bf16=False)
+    assert optim.GRAD_POOL is None and fb.grads.shape == fb.params.shape and float(fb.grads.abs().sum()) == 0.0
+    assert pool.register() is False
+
+
 def test_bench_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU port of the reference step on the host cores) prints exactly one JSON line with
     the contract's keys; it is the one bench leg that runs without a GPU."""
